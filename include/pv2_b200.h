@@ -1,0 +1,139 @@
+/*
+ * pv2_b200.h — C ABI of libpv2_b200.so: the B200 (sm_100a) implementation of the PonderV2
+ * pretraining hot path.  This is the drop-in boundary underneath
+ *   B1  spconv.pytorch            (reference call sites: ponder/models/sparse_unet/spconv_unet_v1m1_base.py:11-278)
+ *   B2  smooth_sampler._C         (reference: libs/smooth-sampler/smooth_sampler/csrc/smooth_sampler.cpp:36-97)
+ *   B3  render_utils (NeuSModel)  (reference: ponder/models/ponder/render_utils/**)
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; the caller (torch) owns
+ *     all buffers including workspaces; nothing in here allocates, frees or synchronises.
+ *   - `stream` is a cudaStream_t passed as void*; work is stream-ordered and re-entrant.
+ *   - return value: 0 on success, a negative PV2_E* code for argument errors, a positive
+ *     cudaError_t for launch errors.  pv2_error_string() maps either to text.
+ *   - feature matrices are row-major [rows, channels] ("channels-last").
+ *   - dtype codes: PV2_F32 = 0, PV2_BF16 = 1, PV2_F64 = 2 (sampler KAT only).
+ */
+#ifndef PV2_B200_H_
+#define PV2_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PV2_F32 0
+#define PV2_BF16 1
+#define PV2_F64 2
+
+#define PV2_EINVAL (-1)   /* bad argument (null pointer, negative size, unsupported shape) */
+#define PV2_EWORKSPACE (-2) /* workspace too small */
+#define PV2_EUNSUPPORTED (-3)
+
+int pv2_version(void);
+const char* pv2_error_string(int code);
+/* Number of SMs the library sized its persistent grids for (148 on B200); 0 if no device. */
+int pv2_sm_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Rulebook (neighbour-map) build.  Replaces spconv's indice-pair generation that the first
+ * SubMConv3d / SparseConv3d of every indice_key triggers
+ * (spconv_unet_v1m1_base.py:47-66,111-119 keys stem/subm0..4; :135-142 keys spconv1..4).
+ * coords: [n,4] int32 rows (batch, c0, c1, c2), all >= 0, c_a < spatial_shape[a].
+ * ------------------------------------------------------------------------------------------ */
+
+/* bytes of workspace for the coordinate hash table used by both rulebook builders */
+size_t pv2_rulebook_workspace_bytes(int64_t n);
+
+/* Submanifold map.  nbr: [ksize^3, n] int32, nbr[k][j] = row i whose coord equals
+ * coord[j] + (k_a - ksize/2) per axis, k = (k0*ksize + k1)*ksize + k2, or -1.
+ * Duplicate coords resolve to the smallest row index.  pair_count (optional, may be NULL):
+ * device int64[1] receiving the number of non-negative entries. */
+int pv2_rulebook_subm(const int32_t* coords, int64_t n, const int32_t* spatial_shape_host,
+                      int ksize, int32_t* nbr, int64_t* pair_count,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* Strided (kernel 2, stride 2, pad 0) map, stage 1.  Output voxels are the distinct
+ * (batch, c>>1) rows, numbered in order of the first input row that maps to them.
+ *   out_coords [n,4] (capacity n; first *n_out rows valid), in2out [n], koff [n] with
+ *   koff = ((c0&1)*2 + (c1&1))*2 + (c2&1); n_out: device int32[1]. */
+int pv2_rulebook_down(const int32_t* coords, int64_t n, const int32_t* spatial_shape_host,
+                      int32_t* out_coords, int32_t* in2out, int32_t* koff, int32_t* n_out,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* Stage 2 (after the caller read n_out): gather maps for both directions.
+ *   nbr_down [8, n_out]: nbr_down[k][j] = fine row i with in2out[i]==j && koff[i]==k, else -1
+ *                        (SparseConv3d fwd, SparseInverseConv3d dgrad)
+ *   nbr_up   [8, n]    : nbr_up[k][i] = in2out[i] if koff[i]==k else -1
+ *                        (SparseInverseConv3d fwd, SparseConv3d dgrad) */
+int pv2_rulebook_down_maps(const int32_t* in2out, const int32_t* koff, int64_t n, int64_t n_out,
+                           int32_t* nbr_down, int32_t* nbr_up, void* stream);
+
+/* batch ids from cumulative offsets (ponder/models/utils.py:11-26 offset2batch) fused with the
+ * [n,4] int32 (batch, c0, c1, c2) assembly of spconv_unet_v1m1_base.py:247-256.
+ * grid_coord: [n,3] int64, offset: [b] int64 cumulative. */
+int pv2_make_indices(const int64_t* grid_coord, const int64_t* offset, int64_t n, int batch,
+                     int32_t* indices, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Sparse convolution arithmetic (gather -> GEMM -> output-stationary accumulate).
+ * Replaces spconv's SubMConv3d / SparseConv3d / SparseInverseConv3d forward, dgrad and wgrad.
+ *   y[j, :] = bias + sum_k W_k * x[nbr[k][j], :]          (rows with nbr == -1 contribute 0)
+ * Weight element (co, k, ci) is read at w[co*w_stride_co + k*w_stride_k + ci] so the same
+ * entry point serves forward (spconv layout [Cout,K,Cin]: strides K*Cin, Cin) and dgrad
+ * (the transposed/k-flipped copy the host shim prepares).
+ * ------------------------------------------------------------------------------------------ */
+int pv2_spconv_gather_gemm(const void* x, const void* w, int64_t w_stride_co, int64_t w_stride_k,
+                           const float* bias, const int32_t* nbr, void* y,
+                           int64_t n_in, int64_t n_out, int cin, int cout, int kvol,
+                           int dtype, void* stream);
+
+/* dw[co, k, ci] (+)= sum_j dy[j, co] * x[nbr[k][j], ci];  dw is float32 [Cout, K, Cin], must be
+ * zeroed by the caller (accumulated with atomics across row chunks). */
+int pv2_spconv_wgrad(const void* x, const void* dy, const int32_t* nbr, float* dw,
+                     int64_t n_in, int64_t n_out, int cin, int cout, int kvol,
+                     int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Densify: voxel features -> dense channels-last volume, scatter-mean
+ * (ponder_indoor_base.py:177-216,332-342; ponder_outdoor_base.py:178-210).
+ * cell: [n] int64 flattened cell id in the OUTPUT memory order, or -1 to drop the row.
+ * volume: [cells, c] float32 (zero-filled here), count: [cells] int32 (zero-filled here).
+ * ------------------------------------------------------------------------------------------ */
+int pv2_densify_fwd(const float* feat, const int64_t* cell, int64_t n, int c, int64_t cells,
+                    float* volume, int32_t* count, void* stream);
+/* dfeat[i,:] = dvolume[cell[i],:] / count[cell[i]] */
+int pv2_densify_bwd(const float* dvolume, const int64_t* cell, const int32_t* count, int64_t n,
+                    int c, float* dfeat, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Trilinear sampler with first and second derivatives (B2).  Same argument meaning as
+ * smooth_sampler._C.forward / backward / backward_backward (smooth_sampler.cpp:36-97):
+ *   input (N,C,D,H,W) contiguous, grid (N,P,3) with P = Do*Ho*Wo, output (N,C,P).
+ *   padding_mode 0 zeros / 1 border / 2 reflection.
+ * dtype PV2_F32 or PV2_F64.
+ * ------------------------------------------------------------------------------------------ */
+int pv2_trilinear_fwd(const void* input, const void* grid, void* output,
+                      int64_t N, int64_t C, int64_t D, int64_t H, int64_t W, int64_t P,
+                      int padding_mode, int align_corners, int apply_smoothstep,
+                      int dtype, void* stream);
+/* grad_input may be NULL (input does not require grad); otherwise zero-filled by the caller. */
+int pv2_trilinear_bwd(const void* grad_output, const void* input, const void* grid,
+                      void* grad_input, void* grad_grid,
+                      int64_t N, int64_t C, int64_t D, int64_t H, int64_t W, int64_t P,
+                      int padding_mode, int align_corners, int apply_smoothstep,
+                      int dtype, void* stream);
+/* grad_out_input may be NULL; grad_input and grad_grad_out are zero-filled by the caller. */
+int pv2_trilinear_bwd_bwd(const void* grad_out_input, const void* grad_out_grid,
+                          const void* input, const void* grid, const void* grad_output,
+                          void* grad_input, void* grad_grid, void* grad_grad_out,
+                          int64_t N, int64_t C, int64_t D, int64_t H, int64_t W, int64_t P,
+                          int padding_mode, int align_corners, int apply_smoothstep,
+                          int dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PV2_B200_H_ */

@@ -1,0 +1,218 @@
+"""Generate golden vectors by running the REFERENCE's own Python code (TEST INFRASTRUCTURE).
+
+Run in the build container only (needs /root/reference):   python -m oracle.gen_golden
+Writes small fixtures to tests/golden/:
+
+  render_<case>.npz   inputs (rays, volume, decoder weights, injected jitter noise) and the outputs, losses and
+                      gradients of the reference's `NeuSModel` (ponder/models/ponder/render_utils/**) with the CUDA-only
+                      `smooth_sampler.SmoothSampler` replaced by oracle/trilinear_oracle.py (itself pinned to
+                      F.grid_sample + gradgradcheck, the reference's own KAT, in tests/test_oracle_cpu.py).
+  spunet_v1m1_state.json   parameter/buffer names and shapes of the reference's `SpUNet-v1m1`
+                      (ponder/models/sparse_unet/spconv_unet_v1m1_base.py) built on top of ponderv2_b200.spconv —
+                      the checkpoint-compatibility contract (hooks/misc.py:208-253).
+
+Third-party modules missing from this image (timm, torch_scatter, torch_geometric, addict, clip, ...) are
+stubbed in sys.modules; none of them is on the arithmetic path exercised here.
+"""
+from __future__ import annotations
+
+import json
+import sys
+import types
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+REF = Path("/root/reference")
+GOLD = ROOT / "tests" / "golden"
+
+
+def _install_stubs():
+    sys.path.insert(0, str(ROOT))
+    from oracle.trilinear_oracle import trilinear_sample
+    import ponderv2_b200.spconv as pv2_spconv
+    import ponderv2_b200.spconv.pytorch as pv2_spconv_pt
+
+    def mod(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+
+    sys.modules["spconv"] = pv2_spconv
+    sys.modules["spconv.pytorch"] = pv2_spconv_pt
+
+    class _Sampler:
+        @staticmethod
+        def apply(input, grid, padding_mode="zeros", align_corners=True, apply_smoothstep=False):
+            return trilinear_sample(input, grid, padding_mode, align_corners, apply_smoothstep)
+
+    mod("smooth_sampler", SmoothSampler=_Sampler)
+    mod("timm"); mod("timm.models"); mod("timm.models.layers", trunc_normal_=torch.nn.init.trunc_normal_)
+    mod("torch_scatter", scatter=None)
+    mod("torch_geometric"); mod("torch_geometric.utils", scatter=None)
+    mod("torch_geometric.nn"); mod("torch_geometric.nn.pool", voxel_grid=None)
+    mod("torch_cluster", knn_graph=None, fps=None)
+    mod("termcolor", colored=lambda s, *a, **k: s)
+    mod("clip")
+    mod("SharedArray")
+    mod("tensorboardX", SummaryWriter=object)
+
+    class _Dict(dict):
+        """minimal addict.Dict: attribute access on nested dicts"""
+
+        def __init__(self, *a, **k):
+            super().__init__()
+            for key, val in dict(*a, **k).items():
+                self[key] = _Dict(val) if isinstance(val, dict) else val
+
+        def __getattr__(self, name):
+            try:
+                return self[name]
+            except KeyError:
+                raise AttributeError(name) from None
+
+        __setattr__ = dict.__setitem__
+
+    mod("addict", Dict=_Dict)
+    sys.path.insert(0, str(REF))
+    return _Dict
+
+
+class _NoiseQueue:
+    """Feeds pre-generated tensors to the reference's `torch.rand` call sites (ray_samplers.py:78-84, 262-268)."""
+
+    def __init__(self, tensors):
+        self.q = list(tensors)
+        self.orig = torch.rand
+
+    def __enter__(self):
+        def fake(*size, **kw):
+            t = self.q.pop(0)
+            want = tuple(size[0]) if len(size) == 1 and isinstance(size[0], (tuple, list)) else tuple(size)
+            assert tuple(t.shape) == want, (t.shape, want)
+            return t.clone()
+        torch.rand = fake
+        return self
+
+    def __exit__(self, *exc):
+        torch.rand = self.orig
+        assert not self.q, "unused noise tensors"
+
+
+CASES = {
+    # indoor (configs/scannet/pretrain-ponder-spunet-v1m1-0-base.py:31-93), shrunk
+    "indoor_train": dict(
+        kind="indoor", training=True, R=24, S0=24, Si=8, vol=(128, 6, 10, 12), seed=11),
+    "indoor_eval": dict(
+        kind="indoor", training=False, R=12, S0=16, Si=8, vol=(128, 5, 7, 9), seed=12),
+    # outdoor (configs/nuscenes/pretrain-ponder-spunet-v1m1-0-base.py), shrunk
+    "outdoor_train": dict(
+        kind="outdoor", training=True, R=20, S0=18, Si=6, vol=(32, 5, 12, 12), seed=13),
+}
+
+
+def renderer_cfg(kind: str, S0: int, Si: int, Dict):
+    if kind == "indoor":
+        field = dict(
+            type="SDFField",
+            sdf_decoder=dict(in_dim=64, out_dim=65, hidden_size=128, n_blocks=1, pos_enc=False, points_factor=0.0),
+            rgb_decoder=dict(in_dim=134, out_dim=3, hidden_size=128, n_blocks=0, pos_enc=False, points_factor=0.0),
+            beta_init=0.3, use_gradient=True, volume_type="default", padding_mode="zeros", share_volume=False,
+            norm_pts=True, norm_padding=0.1)
+        collider = dict(type="AABBBoxCollider", near_plane=0.01, bbox=[-0.55, -0.55, -0.55, 0.55, 0.55, 0.55])
+        loss = Dict(sensor_depth_truncation=0.05, temperature=0.01,
+                    weights=Dict(eikonal_loss=0.01, free_space_loss=1.0, sdf_loss=10.0, depth_loss=1.0, rgb_loss=10.0,
+                                 semantic_loss=0.0))
+    else:
+        field = dict(
+            type="SDFField",
+            sdf_decoder=dict(in_dim=32, out_dim=17, hidden_size=16, n_blocks=5, points_factor=1.0),
+            rgb_decoder=None, semantic_decoder=None,
+            beta_init=0.3, use_gradient=True, volume_type="default", padding_mode="zeros", share_volume=True,
+            norm_pts=False, norm_padding=0.0)
+        collider = dict(type="AABBBoxCollider", near_plane=0.01, bbox=[0, 0, 0, 1, 1, 1])
+        loss = Dict(sensor_depth_truncation=0.05, temperature=0.01,
+                    weights=Dict(eikonal_loss=0.01, free_space_loss=1.0, sdf_loss=10.0, depth_loss=1.0, rgb_loss=0.0,
+                                 semantic_loss=0.0))
+    sampler = dict(type="NeuSSampler", initial_sampler="UniformSampler", num_samples=S0, num_samples_importance=Si,
+                   num_upsample_steps=1, train_stratified=True, single_jitter=False)
+    return dict(type="NeuSModel", field=field, collider=collider, sampler=sampler, loss=loss)
+
+
+def gen_render_case(name: str, spec: dict, Dict) -> None:
+    from ponder.models.ponder.render_utils import RayBundle, build_renderer
+
+    torch.manual_seed(spec["seed"])
+    g = torch.Generator().manual_seed(spec["seed"])
+    model = build_renderer(renderer_cfg(spec["kind"], spec["S0"], spec["Si"], Dict))
+    model.train(spec["training"])
+    R, S0, Si = spec["R"], spec["S0"], spec["Si"]
+    C, Z, Y, X = spec["vol"]
+    volume = torch.randn(C, Z, Y, X, generator=g).requires_grad_(True)
+    if spec["kind"] == "indoor":
+        o = (torch.rand(R, 3, generator=g) - 0.5) * 0.55
+    else:
+        o = 0.25 + 0.5 * torch.rand(R, 3, generator=g)
+    d = torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=-1)
+    # include a ray that misses the box and an axis-parallel one
+    o[0] = torch.tensor([2.0, 2.0, 2.0]); d[0] = torch.tensor([1.0, 0.0, 0.0])
+    d[1] = torch.tensor([0.0, 0.0, 1.0])
+    depth_gt = torch.rand(R, 1, generator=g) * 0.9 + 0.1
+    depth_gt[2] = 0.0  # invalid pixel
+    rgb_gt = torch.rand(R, 3, generator=g)
+    noise_u = torch.rand(R, S0 + 1, generator=g)
+    noise_p = torch.rand(R, Si + 1, generator=g)
+
+    queue = [noise_u, noise_p] if spec["training"] else []
+    with _NoiseQueue(queue):
+        out = model(RayBundle(origins=o.clone(), directions=d.clone()), [volume])
+    targets = {"depth": depth_gt, "rgb": rgb_gt}
+    loss_dict = model.get_loss(out, targets)
+    total = sum(v for k, v in loss_dict.items() if "loss" in k)
+    total.backward()
+
+    arrays = {
+        "rays_o": o, "rays_d": d, "volume": volume.detach(), "depth_gt": depth_gt, "rgb_gt": rgb_gt,
+        "noise_uniform": noise_u, "noise_pdf": noise_p, "total_loss": total.detach(),
+        "grad_volume": volume.grad,
+    }
+    for k, v in out.items():
+        arrays["out." + k] = v.detach()
+    for k, v in loss_dict.items():
+        arrays["loss." + k] = v.detach()
+    for k, v in model.state_dict().items():
+        arrays["param." + k] = v.detach()
+    for k, p in model.named_parameters():
+        if p.grad is not None:
+            arrays["grad." + k] = p.grad
+    meta = dict(kind=spec["kind"], training=spec["training"], R=R, S0=S0, Si=Si)
+    np.savez_compressed(GOLD / f"render_{name}.npz", meta=json.dumps(meta),
+                        **{k: v.numpy() for k, v in arrays.items()})
+    print(f"render_{name}: total loss {float(total):.6f}, {len(arrays)} arrays")
+
+
+def gen_spunet_state() -> None:
+    from ponder.models.sparse_unet.spconv_unet_v1m1_base import SpUNetBase
+
+    torch.manual_seed(0)
+    m = SpUNetBase(in_channels=6, num_classes=0, channels=(32, 64, 128, 256, 256, 128, 96, 96),
+                   layers=(2, 3, 4, 6, 2, 2, 2, 2))
+    state = {k: list(v.shape) for k, v in m.state_dict().items()}
+    n_conv = sum(int(np.prod(s)) for k, s in state.items() if k.endswith("weight") and len(s) == 5)
+    (GOLD / "spunet_v1m1_state.json").write_text(json.dumps({"state": state, "conv_params": n_conv}, indent=0))
+    print(f"spunet_v1m1_state: {len(state)} entries, {n_conv} conv parameters")
+
+
+def main() -> None:
+    GOLD.mkdir(parents=True, exist_ok=True)
+    Dict = _install_stubs()
+    for name, spec in CASES.items():
+        gen_render_case(name, spec, Dict)
+    gen_spunet_state()
+
+
+if __name__ == "__main__":
+    main()

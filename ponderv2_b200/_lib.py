@@ -1,0 +1,101 @@
+"""ctypes binding of libpv2_b200.so (the C ABI declared in include/pv2_b200.h).
+
+There is no CPU fallback: if the library is missing, or a call is made without a CUDA tensor,
+the failure is loud (RuntimeError).  Loading the library itself needs no GPU, so the symbol
+table can be checked on a CPU-only box.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_LIB_PATH = Path(__file__).resolve().parent / "lib" / "libpv2_b200.so"
+_lib = None
+
+_i32p = C.c_void_p
+_vp = C.c_void_p
+_i64 = C.c_int64
+_int = C.c_int
+_sz = C.c_size_t
+
+# name -> (restype, argtypes); must list every symbol declared in include/pv2_b200.h
+SIGNATURES = {
+    "pv2_version": (_int, []),
+    "pv2_error_string": (C.c_char_p, [_int]),
+    "pv2_sm_count": (_int, []),
+    "pv2_rulebook_workspace_bytes": (_sz, [_i64]),
+    "pv2_rulebook_subm": (_int, [_vp, _i64, C.POINTER(C.c_int32), _int, _vp, _vp, _vp, _sz, _vp]),
+    "pv2_rulebook_down": (_int, [_vp, _i64, C.POINTER(C.c_int32), _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "pv2_rulebook_down_maps": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp]),
+    "pv2_make_indices": (_int, [_vp, _vp, _i64, _int, _vp, _vp]),
+    "pv2_spconv_gather_gemm": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _i64, _int, _int, _int, _int, _vp]),
+    "pv2_spconv_wgrad": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _int, _int, _int, _int, _vp]),
+    "pv2_densify_fwd": (_int, [_vp, _vp, _i64, _int, _i64, _vp, _vp, _vp]),
+    "pv2_densify_bwd": (_int, [_vp, _vp, _vp, _i64, _int, _vp, _vp]),
+    "pv2_trilinear_fwd": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _int, _int, _int, _int, _vp]),
+    "pv2_trilinear_bwd": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _int, _int, _int, _int, _vp]),
+    "pv2_trilinear_bwd_bwd": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64,
+                                     _int, _int, _int, _int, _vp]),
+}
+
+
+def lib_path() -> Path:
+    return _LIB_PATH
+
+
+def load():
+    """Load (once) and return the ctypes library; raises RuntimeError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _LIB_PATH.exists():
+        raise RuntimeError(
+            f"{_LIB_PATH} is missing: build it with `python -m ponderv2_b200.build` "
+            "(ponderv2_b200 has no CPU or eager fallback)")
+    lib = C.CDLL(str(_LIB_PATH))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError -> the .so is stale
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(code: int, what: str) -> None:
+    if code != 0:
+        msg = load().pv2_error_string(code)
+        raise RuntimeError(f"{what} failed ({code}): {msg.decode() if msg else '?'}")
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (None -> NULL).  The tensor must be CUDA + contiguous."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("ponderv2_b200 kernels need CUDA tensors (there is no CPU fallback)")
+    if not t.is_contiguous():
+        raise RuntimeError("ponderv2_b200 kernels need contiguous tensors")
+    return C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def i32x3(vals):
+    arr = (C.c_int32 * 3)(*[int(v) for v in vals])
+    return arr
+
+
+DTYPE_CODE = {}
+
+
+def dtype_code(dt) -> int:
+    import torch
+    if not DTYPE_CODE:
+        DTYPE_CODE.update({torch.float32: 0, torch.bfloat16: 1, torch.float64: 2})
+    try:
+        return DTYPE_CODE[dt]
+    except KeyError:
+        raise RuntimeError(f"unsupported dtype {dt}") from None

@@ -1,0 +1,39 @@
+// Library-level entry points and the dispatcher between the tensor-core and SIMT sparse-conv kernels.
+#include "pv2_common.cuh"
+
+extern "C" {
+
+int pv2_spconv_gather_gemm_simt(const void*, const void*, int64_t, int64_t, const float*, const int32_t*, void*, int64_t,
+                                int64_t, int, int, int, int, void*);
+int pv2_spconv_wgrad_simt(const void*, const void*, const int32_t*, float*, int64_t, int64_t, int, int, int, int, void*);
+
+int pv2_version(void) { return 100; }
+
+const char* pv2_error_string(int code) {
+  if (code == 0) return "ok";
+  if (code == PV2_EINVAL) return "pv2: invalid argument";
+  if (code == PV2_EWORKSPACE) return "pv2: workspace too small";
+  if (code == PV2_EUNSUPPORTED) return "pv2: unsupported dtype/shape";
+  if (code > 0) return cudaGetErrorString((cudaError_t)code);
+  return "pv2: unknown error";
+}
+
+int pv2_sm_count(void) {
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+  return sms;
+}
+
+int pv2_spconv_gather_gemm(const void* x, const void* w, int64_t w_sco, int64_t w_sk, const float* bias,
+                           const int32_t* nbr, void* y, int64_t n_in, int64_t n_out, int cin, int cout, int kvol,
+                           int dtype, void* stream) {
+  return pv2_spconv_gather_gemm_simt(x, w, w_sco, w_sk, bias, nbr, y, n_in, n_out, cin, cout, kvol, dtype, stream);
+}
+
+int pv2_spconv_wgrad(const void* x, const void* dy, const int32_t* nbr, float* dw, int64_t n_in, int64_t n_out, int cin,
+                     int cout, int kvol, int dtype, void* stream) {
+  return pv2_spconv_wgrad_simt(x, dy, nbr, dw, n_in, n_out, cin, cout, kvol, dtype, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,29 @@
+"""Helpers shared by the parity tests: load a tests/golden/render_*.npz fixture into oracle objects."""
+import json
+from pathlib import Path
+
+import numpy as np
+import torch
+
+GOLD = Path(__file__).resolve().parent / "golden"
+
+
+def load_render_case(name: str, dtype=torch.float32):
+    from oracle.render_oracle import RenderConfig
+
+    z = np.load(GOLD / f"render_{name}.npz")
+    meta = json.loads(str(z["meta"]))
+    arr = {k: torch.from_numpy(z[k]) for k in z.files if k != "meta"}
+    sd = {k[len("param."):]: v.to(dtype) for k, v in arr.items() if k.startswith("param.")}
+    if meta["kind"] == "indoor":
+        cfg = RenderConfig(bbox=[-0.55] * 3 + [0.55] * 3, near_plane=0.01, num_samples=meta["S0"],
+                           num_samples_importance=meta["Si"], share_volume=False, norm_pts=True, norm_padding=0.1,
+                           sdf_points_factor=0.0, rgb_points_factor=0.0, has_rgb=True,
+                           loss_weights=dict(eikonal_loss=0.01, free_space_loss=1.0, sdf_loss=10.0, depth_loss=1.0,
+                                             rgb_loss=10.0))
+    else:
+        cfg = RenderConfig(bbox=[0, 0, 0, 1, 1, 1], near_plane=0.01, num_samples=meta["S0"],
+                           num_samples_importance=meta["Si"], share_volume=True, norm_pts=False, norm_padding=0.0,
+                           sdf_points_factor=1.0, has_rgb=False,
+                           loss_weights=dict(eikonal_loss=0.01, free_space_loss=1.0, sdf_loss=10.0, depth_loss=1.0))
+    return meta, arr, sd, cfg
