@@ -1,0 +1,331 @@
+"""GPU parity of the B200 kernels against the CPU oracle, through the C ABI (ctypes) and the B1/B2 shims.
+
+Integer results (rulebooks) are compared bit-exactly in canonical form; floating point within the stated
+tolerances: fp32 kernels <= 2e-5 relative to the fp64 oracle's magnitude (fp32 accumulation-order noise), bf16
+storage <= 2e-2.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import densify_oracle as do
+from oracle import spconv_oracle as so
+from oracle.trilinear_oracle import trilinear_sample
+from ponderv2_b200 import synth
+
+
+def _dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+def _random_cloud(n, extent, batch, seed):
+    rng = np.random.default_rng(seed)
+    pts = set()
+    while len(pts) < n:
+        pts.add((int(rng.integers(0, batch)), *[int(v) for v in rng.integers(0, extent, size=3)]))
+    arr = np.array(sorted(pts), dtype=np.int32).reshape(-1, 4)
+    rng.shuffle(arr)
+    return arr
+
+
+def _indoor_indices(n, seed):
+    c = synth.indoor_cloud(n, seed)
+    ind = np.concatenate([np.zeros((n, 1), np.int64), c["grid_coord"]], 1).astype(np.int32)
+    return ind, (c["grid_coord"].max(0) + 96).tolist()
+
+
+# ------------------------------------------------------------------------------------------ rulebooks
+@pytest.mark.parametrize("ksize", [3, 5])
+@pytest.mark.parametrize("case", ["random_b2", "indoor_5k", "single", "dense_block"])
+def test_subm_rulebook_bit_exact(cuda_lib, ksize, case):
+    from ponderv2_b200.spconv.pytorch import build_subm_rulebook
+    if case == "random_b2":
+        ind, shape = _random_cloud(3000, 24, 2, 5), [30, 30, 30]
+    elif case == "indoor_5k":
+        ind, shape = _indoor_indices(5000, 7)
+    elif case == "single":
+        ind, shape = np.array([[0, 3, 4, 5]], dtype=np.int32), [8, 8, 8]
+    else:  # every site occupied, touching the boundary of the spatial shape
+        g = np.stack(np.meshgrid(np.arange(6), np.arange(5), np.arange(4), indexing="ij"), -1).reshape(-1, 3)
+        ind, shape = np.concatenate([np.zeros((g.shape[0], 1)), g], 1).astype(np.int32), [6, 5, 4]
+    rb = build_subm_rulebook(torch.from_numpy(ind).to(_dev()), shape, ksize)
+    ref = so.subm_rulebook(ind, shape, ksize)
+    got = rb.nbr.cpu().numpy()
+    assert got.dtype == np.int32 and got.shape == ref.shape
+    assert np.array_equal(got, ref)
+    assert rb.num_pairs == int((ref >= 0).sum())
+
+
+def test_subm_rulebook_empty_and_duplicates(cuda_lib):
+    from ponderv2_b200.spconv.pytorch import build_subm_rulebook
+    empty = torch.zeros((0, 4), dtype=torch.int32, device=_dev())
+    rb = build_subm_rulebook(empty, [4, 4, 4], 3)
+    assert rb.nbr.shape == (27, 0)
+    dup = np.array([[0, 1, 1, 1], [0, 1, 1, 2], [0, 1, 1, 1]], dtype=np.int32)  # rows 0 and 2 collide
+    rb = build_subm_rulebook(torch.from_numpy(dup).to(_dev()), [4, 4, 4], 3)
+    assert np.array_equal(rb.nbr.cpu().numpy(), so.subm_rulebook(dup, [4, 4, 4], 3))
+
+
+@pytest.mark.parametrize("case", ["random_b3", "indoor_20k", "odd_shape"])
+def test_down_rulebook_canonical_bit_exact(cuda_lib, case):
+    from ponderv2_b200.spconv.pytorch import build_down_rulebook
+    if case == "random_b3":
+        ind, shape = _random_cloud(4000, 21, 3, 9), [24, 24, 24]
+    elif case == "indoor_20k":
+        ind, shape = _indoor_indices(20000, 3)
+    else:
+        ind, shape = _random_cloud(500, 9, 1, 4), [9, 9, 9]  # last plane has no complete window -> dropped
+    rb = build_down_rulebook(torch.from_numpy(ind).to(_dev()), shape)
+    ref_out, ref_i2o, ref_koff, ref_shape = so.down_rulebook(ind, shape)
+    assert rb.out_shape == ref_shape
+    out = rb.out_indices.cpu().numpy()
+    i2o = rb.in2out.cpu().numpy()
+    # implementation order: outputs numbered by first contributing input row
+    firsts = {}
+    for i, o in enumerate(i2o.tolist()):
+        if o >= 0:
+            firsts.setdefault(o, i)
+    order = sorted(firsts, key=lambda o: firsts[o])
+    assert order == list(range(len(order)))
+    can_out, can_i2o, perm = so.canonical_down(out, i2o, ref_shape)
+    assert np.array_equal(can_out, ref_out)
+    assert np.array_equal(can_i2o, ref_i2o)
+    assert np.array_equal(rb.koff.cpu().numpy(), ref_koff)
+    nd, nu = so.down_maps(i2o, ref_koff, out.shape[0])
+    assert np.array_equal(rb.nbr_down.cpu().numpy(), nd)
+    assert np.array_equal(rb.nbr_up.cpu().numpy(), nu)
+
+
+def test_make_indices(cuda_lib):
+    from ponderv2_b200.backbone import make_sparse_indices
+    gc = torch.randint(0, 50, (1000, 3), dtype=torch.int64)
+    offset = torch.tensor([100, 100, 640, 1000], dtype=torch.int64)  # an empty scene in the middle
+    got = make_sparse_indices(gc.to(_dev()), offset.to(_dev())).cpu()
+    batch = torch.from_numpy(so.offset2batch(offset.numpy()))
+    assert torch.equal(got, torch.cat([batch[:, None].int(), gc.int()], 1))
+
+
+# ------------------------------------------------------------------------------------------ sparse conv arithmetic
+def _conv_case(kind, cin, cout, dtype, seed, n=1500):
+    """Runs one conv forward+backward on GPU (product) and CPU (oracle, fp64); returns max relative errors."""
+    import ponderv2_b200.spconv.pytorch as spconv
+    dev = _dev()
+    torch.manual_seed(seed)
+    ind = _random_cloud(n, 16, 2, seed)
+    shape = [20, 20, 20]
+    x64 = torch.randn(n, cin, dtype=torch.float64)
+    if kind == "subm3":
+        mod = spconv.SubMConv3d(cin, cout, 3, padding=1, bias=True, indice_key="k")
+    elif kind == "subm5":
+        mod = spconv.SubMConv3d(cin, cout, 5, padding=1, bias=False, indice_key="k")
+    elif kind == "subm1":
+        mod = spconv.SubMConv3d(cin, cout, 1, bias=False)
+    elif kind in ("down", "updown"):
+        mod = spconv.SparseConv3d(cin, cout, 2, stride=2, bias=False, indice_key="d")
+    mod = mod.to(dev)
+    w64 = mod.weight.detach().cpu().double().requires_grad_(True)
+    b64 = mod.bias.detach().cpu().double().requires_grad_(True) if mod.bias is not None else None
+    xg = x64.to(dev, dtype).requires_grad_(True)
+    xo = x64.clone()
+    if dtype == torch.bfloat16:  # compare against the oracle fed with the same rounded inputs
+        xo = xg.detach().cpu().double()
+        w64 = mod.weight.detach().to(torch.bfloat16).cpu().double().requires_grad_(True)
+    xo.requires_grad_(True)
+    st = spconv.SparseConvTensor(xg, torch.from_numpy(ind).to(dev), shape, 2)
+    ctx = torch.autocast("cuda", dtype=torch.bfloat16) if dtype == torch.bfloat16 else torch.autocast("cuda", enabled=False)
+    with ctx:
+        out = mod(st)
+    yo_t = None
+    ot = so.OracleSparseTensor(xo, ind, shape, 2)
+    if kind.startswith("subm"):
+        ks = int(kind[-1])
+        yo = so.subm_conv(ot, w64, b64, ks, "k").features
+        yg = out.features
+    else:
+        o_down = so.down_conv(ot, w64, None, "d")
+        # bring product rows into canonical order
+        _, _, perm = so.canonical_down(out.indices.cpu().numpy(), np.zeros(0, np.int32), o_down.spatial_shape)
+        perm_t = torch.from_numpy(perm).to(dev)
+        yg = out.features[perm_t]
+        yo = o_down.features
+        if kind == "updown":
+            inv = spconv.SparseInverseConv3d(cout, cin, 2, indice_key="d", bias=False).to(dev)
+            wi64 = inv.weight.detach().cpu().double().requires_grad_(True)
+            if dtype == torch.bfloat16:
+                wi64 = inv.weight.detach().to(torch.bfloat16).cpu().double().requires_grad_(True)
+            with ctx:
+                out2 = inv(out)
+            yg = out2.features
+            yo = so.inverse_conv(o_down, wi64, None, "d").features
+            assert torch.equal(out2.indices.cpu(), torch.from_numpy(ind))
+    g64 = torch.randn(yo.shape, dtype=torch.float64)
+    yo.backward(g64)
+    yg.backward(g64.to(dev, yg.dtype))
+    scale = lambda t: max(t.abs().max().item(), 1e-6)
+    errs = {
+        "y": (yg.detach().cpu().double() - yo.detach()).abs().max().item() / scale(yo),
+        "dx": (xg.grad.cpu().double() - xo.grad).abs().max().item() / scale(xo.grad),
+        "dw": (mod.weight.grad.cpu().double() - w64.grad).abs().max().item() / scale(w64.grad),
+    }
+    if b64 is not None and dtype == torch.float32:
+        errs["db"] = (mod.bias.grad.cpu().double() - b64.grad).abs().max().item() / scale(b64.grad)
+    return errs
+
+
+@pytest.mark.parametrize("kind,cin,cout", [
+    ("subm3", 32, 32), ("subm3", 64, 96), ("subm3", 192, 128), ("subm5", 6, 32), ("subm1", 128, 96),
+    ("subm3", 7, 13), ("down", 32, 64), ("updown", 64, 96), ("subm5", 4, 32),
+])
+def test_sparse_conv_fp32(cuda_lib, kind, cin, cout):
+    errs = _conv_case(kind, cin, cout, torch.float32, seed=cin + cout)
+    for k, v in errs.items():
+        assert v < 2e-5, (k, v, errs)
+
+
+@pytest.mark.parametrize("kind,cin,cout", [("subm3", 32, 32), ("subm3", 96, 96), ("down", 32, 64), ("updown", 64, 32)])
+def test_sparse_conv_bf16(cuda_lib, kind, cin, cout):
+    errs = _conv_case(kind, cin, cout, torch.bfloat16, seed=cin + cout)
+    for k, v in errs.items():
+        assert v < 2e-2, (k, v, errs)
+
+
+def test_spunet_backbone_matches_oracle(cuda_lib):
+    """Whole SpUNet-v1m1 (59 convs, 10 rulebooks) on an 8 k-voxel two-scene batch: features and parameter grads."""
+    from ponderv2_b200.backbone import SpUNetBase
+    dev = _dev()
+    torch.manual_seed(0)
+    a, b = synth.indoor_cloud(4800, 21), synth.indoor_cloud(3200, 22)
+    gc = np.concatenate([a["grid_coord"], b["grid_coord"]])
+    feat = np.concatenate([a["feat"], b["feat"]])
+    offset = np.array([4800, 8000], dtype=np.int64)
+    model = SpUNetBase(in_channels=6, num_classes=0).to(dev).train()
+    sd = {k: v.detach().cpu().double() for k, v in model.state_dict().items()}
+    for k, v in sd.items():
+        if v.is_floating_point() and ("weight" in k or "bias" in k):
+            v.requires_grad_(True)
+    out = model({"grid_coord": torch.from_numpy(gc).to(dev), "feat": torch.from_numpy(feat).to(dev),
+                 "offset": torch.from_numpy(offset).to(dev)})
+    ref = so.spunet_forward(sd, gc, torch.from_numpy(feat).double(), offset)
+    assert out.shape == (8000, 96)
+    err = (out.detach().cpu().double() - ref.detach()).abs().max().item() / ref.abs().max().item()
+    assert err < 1e-4, err
+    g = torch.randn(ref.shape, dtype=torch.float64, generator=torch.Generator().manual_seed(1))
+    ref.backward(g)
+    out.backward(g.to(dev, torch.float32))
+    worst, worst_name = 0.0, ""
+    for name, p in model.named_parameters():
+        rg = sd[name].grad
+        e = (p.grad.cpu().double() - rg).norm().item() / max(rg.norm().item(), 1e-9)
+        if e > worst:
+            worst, worst_name = e, name
+    # train-mode BN over the handful of rows left at the deepest level amplifies fp32 rounding
+    assert worst < 5e-3, (worst_name, worst)
+
+
+def test_spunet_state_dict_contract(cuda_lib):
+    """Parameter/buffer names and shapes equal the reference's SpUNet-v1m1 (checkpoint compatibility)."""
+    import json
+    from pathlib import Path
+    from ponderv2_b200.backbone import SpUNetBase
+    want = json.loads((Path(__file__).parent / "golden" / "spunet_v1m1_state.json").read_text())["state"]
+    got = {k: list(v.shape) for k, v in SpUNetBase(in_channels=6, num_classes=0).state_dict().items()}
+    assert got == want
+
+
+# ------------------------------------------------------------------------------------------ densify
+def test_densify_indoor_and_outdoor(cuda_lib):
+    from ponderv2_b200 import densify
+    dev = _dev()
+    torch.manual_seed(0)
+    a, b = synth.indoor_cloud(4000, 31), synth.indoor_cloud(2500, 32)
+    coord = torch.from_numpy(np.concatenate([a["coord"], b["coord"]]))
+    offset = np.array([4000, 6500])
+    feat = torch.randn(6500, 24, dtype=torch.float32)
+    grid_shape, grid_size = (16, 16, 8), 0.02
+    res = torch.tensor([int(a["grid_coord"].max()), int(b["grid_coord"].max())])
+    ref_in = feat.clone().double().requires_grad_(True)
+    ref = do.to_dense_indoor(coord.double(), ref_in, offset, res, grid_shape, grid_size)
+    batch = torch.from_numpy(so.offset2batch(offset)).to(dev)
+    f = feat.to(dev).requires_grad_(True)
+    cell = densify.indoor_cells(coord.to(dev), batch, res, grid_shape, grid_size)
+    vol = densify.scatter_mean_volume(f, cell, 2, (grid_shape[2], grid_shape[1], grid_shape[0]))
+    assert vol.shape == ref.shape and vol.is_contiguous(memory_format=torch.channels_last_3d)
+    assert (vol.detach().cpu().double() - ref.detach()).abs().max().item() < 1e-5
+    g = torch.randn(ref.shape, dtype=torch.float64)
+    ref.backward(g)
+    vol.backward(g.to(dev, torch.float32))
+    assert (f.grad.cpu().double() - ref_in.grad).abs().max().item() < 1e-5
+    # outdoor
+    c = synth.outdoor_cloud(5000, 33)
+    bbox, gsz, gshape = [0, 0, 0, 108, 108, 8], [0.6, 0.6, 1.6], [180, 180, 5]
+    fo = torch.randn(5000, 16)
+    ref_o = do.to_dense_outdoor(torch.from_numpy(c["coord"]), fo, np.array([5000]), bbox, gsz, gshape)
+    cell = densify.outdoor_cells(torch.from_numpy(c["coord"]).to(dev), torch.zeros(5000, dtype=torch.int64, device=dev),
+                                 bbox, gsz, gshape)
+    vo = densify.scatter_mean_volume(fo.to(dev), cell, 1, (5, 180, 180))
+    assert (vo.cpu() - ref_o).abs().max().item() < 1e-5
+
+
+# ------------------------------------------------------------------------------------------ trilinear sampler (B2)
+@pytest.mark.parametrize("padding_mode", ["zeros", "border", "reflection"])
+@pytest.mark.parametrize("align_corners", [True, False])
+def test_smooth_sampler_reference_kat(cuda_lib, padding_mode, align_corners):
+    """The reference's own self-check, libs/smooth-sampler/smooth_sampler/modules.py:104-156, verbatim protocol."""
+    from ponderv2_b200.smooth_sampler import SmoothSampler
+    dev = _dev()
+    torch.manual_seed(3)
+    inp = torch.rand([2, 2, 2, 3, 11], device=dev).requires_grad_(True)
+    grid = (torch.rand([2, 2, 1, 5, 3], device=dev) * 2.0 - 1.0).requires_grad_(True)
+    out1 = SmoothSampler.apply(inp, grid, padding_mode, align_corners, False)
+    out2 = torch.nn.functional.grid_sample(inp, grid, padding_mode=padding_mode, align_corners=align_corners)
+    assert torch.allclose(out1, out2)
+    g1 = torch.autograd.grad(out1, [inp, grid], torch.ones_like(out1), create_graph=True)
+    g2 = torch.autograd.grad(out2, [inp, grid], torch.ones_like(out2), create_graph=True)
+    assert torch.allclose(g1[0], g2[0]) and torch.allclose(g1[1], g2[1])
+    for smooth in [True, False]:
+        i64 = torch.rand([2, 2, 2, 3, 11], device=dev).double().requires_grad_(True)
+        g64 = (torch.rand([2, 2, 1, 5, 3], device=dev) * 2.0 - 1.0).double().requires_grad_(True)
+        torch.autograd.gradcheck(SmoothSampler.apply, [i64, g64, padding_mode, align_corners, smooth],
+                                 eps=1e-4, atol=1e-3, rtol=1e-2)
+        torch.autograd.gradgradcheck(SmoothSampler.apply, [i64, g64, padding_mode, align_corners, smooth],
+                                     eps=1e-4, atol=1e-3, rtol=1e-2)
+
+
+@pytest.mark.parametrize("smooth", [False, True])
+def test_smooth_sampler_double_backward_vs_oracle(cuda_lib, smooth):
+    """Second-order path as the renderer uses it: d/dtheta of a loss on (features, d features/d points)."""
+    from ponderv2_b200.smooth_sampler import SmoothSampler
+    dev = _dev()
+    torch.manual_seed(5)
+    vol = torch.randn(1, 8, 5, 6, 7, dtype=torch.float64)
+    grid = torch.rand(1, 1, 9, 13, 3, dtype=torch.float64) * 2.6 - 1.3  # some points outside: zeros padding
+    wmix = torch.randn(8, dtype=torch.float64)
+
+    def run(sampler, v, g):
+        v = v.clone().requires_grad_(True)
+        g = g.clone().requires_grad_(True)
+        f = sampler(v, g)                                        # (1,C,1,R,S)
+        s = (f * wmix.to(f.device).view(1, -1, 1, 1, 1)).sum(1).tanh()
+        dg = torch.autograd.grad(s.sum(), g, create_graph=True)[0]
+        loss = (dg.norm(dim=-1) - 1).pow(2).mean() + s.pow(2).mean() + (f ** 2).mean()
+        loss.backward()
+        return loss.detach().cpu(), v.grad.cpu(), g.grad.cpu()
+
+    lo, gvo, ggo = run(lambda v, g: trilinear_sample(v, g, "zeros", True, smooth), vol, grid)
+    lg, gvg, ggg = run(lambda v, g: SmoothSampler.apply(v, g, "zeros", True, smooth), vol.to(dev), grid.to(dev))
+    assert abs(lo.item() - lg.item()) < 1e-10
+    assert (gvo - gvg).abs().max().item() < 1e-10
+    assert (ggo - ggg).abs().max().item() < 1e-9
+
+
+def test_smooth_sampler_rejects_cpu_and_noncontiguous(cuda_lib):
+    from ponderv2_b200.smooth_sampler import SmoothSampler
+    with pytest.raises(RuntimeError):
+        SmoothSampler.apply(torch.rand(1, 2, 3, 3, 3), torch.rand(1, 1, 1, 4, 3), "zeros", True, False)
+    dev = _dev()
+    with pytest.raises(RuntimeError):
+        SmoothSampler.apply(torch.rand(1, 2, 3, 3, 6, device=dev)[..., ::2], torch.rand(1, 1, 1, 4, 3, device=dev),
+                            "zeros", True, False)
