@@ -34,6 +34,8 @@ extern "C" {
 
 int pv2_version(void);
 const char* pv2_error_string(int code);
+/* Total number of CUDA kernels this library has launched in the calling process (statistics only). */
+int64_t pv2_launch_count(void);
 /* Number of SMs the library sized its persistent grids for (148 on B200); 0 if no device. */
 int pv2_sm_count(void);
 

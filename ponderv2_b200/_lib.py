@@ -23,6 +23,7 @@ SIGNATURES = {
     "pv2_version": (_int, []),
     "pv2_error_string": (C.c_char_p, [_int]),
     "pv2_sm_count": (_int, []),
+    "pv2_launch_count": (_i64, []),
     "pv2_rulebook_workspace_bytes": (_sz, [_i64]),
     "pv2_rulebook_subm": (_int, [_vp, _i64, C.POINTER(C.c_int32), _int, _vp, _vp, _vp, _sz, _vp]),
     "pv2_rulebook_down": (_int, [_vp, _i64, C.POINTER(C.c_int32), _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
@@ -99,3 +100,57 @@ def dtype_code(dt) -> int:
         return DTYPE_CODE[dt]
     except KeyError:
         raise RuntimeError(f"unsupported dtype {dt}") from None
+
+
+# ---------------------------------------------------------------------------------------------
+# optional per-call timing (used by bench.py for the roofline of the dominant kernel)
+# ---------------------------------------------------------------------------------------------
+class _Profile:
+    def __init__(self):
+        self.enabled_for = None   # set of C-ABI names to time, or None
+        self.records = []         # (name, start_event, end_event, algorithmic_bytes, flops)
+
+    def start(self, names):
+        self.enabled_for = set(names)
+        self.records = []
+
+    def stop(self):
+        self.enabled_for = None
+
+    def summary(self):
+        """{name: dict(calls, ms, bytes, flops)} - call after torch.cuda.synchronize()."""
+        out = {}
+        for name, e0, e1, nbytes, flops in self.records:
+            d = out.setdefault(name, dict(calls=0, ms=0.0, bytes=0, flops=0))
+            d["calls"] += 1
+            d["ms"] += e0.elapsed_time(e1)
+            d["bytes"] += nbytes
+            d["flops"] += flops
+        return out
+
+
+PROFILE = _Profile()
+
+
+class timed:
+    """with timed("pv2_x", bytes, flops): <C-ABI call>  — records CUDA events on the launching stream when enabled."""
+
+    __slots__ = ("name", "nbytes", "flops", "e0")
+
+    def __init__(self, name, nbytes=0, flops=0):
+        self.name, self.nbytes, self.flops, self.e0 = name, nbytes, flops, None
+
+    def __enter__(self):
+        if PROFILE.enabled_for is not None and self.name in PROFILE.enabled_for:
+            import torch
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.e0 is not None:
+            import torch
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            PROFILE.records.append((self.name, self.e0, e1, self.nbytes, self.flops))
+        return False

@@ -7,6 +7,10 @@ int pv2_spconv_gather_gemm_simt(const void*, const void*, int64_t, int64_t, cons
                                 int64_t, int, int, int, int, void*);
 int pv2_spconv_wgrad_simt(const void*, const void*, const int32_t*, float*, int64_t, int64_t, int, int, int, int, void*);
 
+static unsigned long long g_launches = 0;
+void pv2_note_launches(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
+int64_t pv2_launch_count(void) { return (int64_t)__atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
 int pv2_version(void) { return 100; }
 
 const char* pv2_error_string(int code) {

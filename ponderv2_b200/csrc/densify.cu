@@ -98,8 +98,7 @@ int pv2_densify_fwd(const float* feat, const int64_t* cell, int64_t n, int c, in
     scatter_mean_v4_kernel<<<pv2_grid_for(n * (c / 4), 256), 256, 0, stream>>>(feat, cell, count, n, c / 4, cells, volume);
   else
     scatter_mean_scalar_kernel<<<pv2_grid_for(n * c, 256), 256, 0, stream>>>(feat, cell, count, n, c, cells, volume);
-  PV2_LAUNCH_OK();
-  return 0;
+  PV2_DONE(3);
 }
 
 int pv2_densify_bwd(const float* dvolume, const int64_t* cell, const int32_t* count, int64_t n, int c, float* dfeat,
@@ -108,8 +107,7 @@ int pv2_densify_bwd(const float* dvolume, const int64_t* cell, const int32_t* co
   if (n == 0) return 0;
   PV2_CHECK_ARG(dvolume && cell && count && dfeat);
   gather_mean_kernel<<<pv2_grid_for(n * c, 256), 256, 0, (cudaStream_t)stream_>>>(dvolume, cell, count, n, c, dfeat);
-  PV2_LAUNCH_OK();
-  return 0;
+  PV2_DONE(1);
 }
 
 }  // extern "C"

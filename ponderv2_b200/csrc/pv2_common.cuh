@@ -8,6 +8,9 @@
 #define PV2_SM_COUNT 148  // B200: 2 dies x 74 SMs; persistent grids are sized in multiples of this
 
 #define PV2_CHECK_ARG(cond) do { if (!(cond)) return PV2_EINVAL; } while (0)
+// launch statistics (relaxed atomic counter, read by bench.py through pv2_launch_count)
+extern "C" void pv2_note_launches(int n);
+#define PV2_DONE(nlaunch) do { pv2_note_launches(nlaunch); cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return (int)e__; return 0; } while (0)
 #define PV2_LAUNCH_OK() do { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return (int)e__; } while (0)
 
 static inline int pv2_grid_for(int64_t work_items, int threads, int max_waves = 8) {

@@ -308,8 +308,7 @@ int pv2_rulebook_subm(const int32_t* coords, int64_t n, const int32_t* shape, in
     probe_subm_kernel<3><<<grid, 256, 0, stream>>>((const int4*)coords, n, shape[0], shape[1], shape[2], t, nbr, (unsigned long long*)pair_count);
   else
     probe_subm_kernel<5><<<grid, 256, 0, stream>>>((const int4*)coords, n, shape[0], shape[1], shape[2], t, nbr, (unsigned long long*)pair_count);
-  PV2_LAUNCH_OK();
-  return 0;
+  PV2_DONE(3);
 }
 
 int pv2_rulebook_down(const int32_t* coords, int64_t n, const int32_t* shape, int32_t* out_coords, int32_t* in2out,
@@ -334,8 +333,7 @@ int pv2_rulebook_down(const int32_t* coords, int64_t n, const int32_t* shape, in
   scan_bsum_kernel<<<1, 1024, 0, stream>>>(bsum, nb, n_out);
   rank_kernel<<<nb, kScanThreads, 0, stream>>>(in2out, t.vals, n, bsum, rank);
   finalize_down_kernel<<<pv2_grid_for(n, 256), 256, 0, stream>>>((const int4*)coords, n, t.vals, rank, in2out, koff, (int4*)out_coords);
-  PV2_LAUNCH_OK();
-  return 0;
+  PV2_DONE(6);
 }
 
 int pv2_rulebook_down_maps(const int32_t* in2out, const int32_t* koff, int64_t n, int64_t n_out, int32_t* nbr_down,
@@ -346,8 +344,7 @@ int pv2_rulebook_down_maps(const int32_t* in2out, const int32_t* koff, int64_t n
   cudaStream_t stream = (cudaStream_t)stream_;
   if (n_out > 0) fill_i32_kernel<<<pv2_grid_for(8 * n_out, 256), 256, 0, stream>>>(nbr_down, 8 * n_out, -1);
   down_maps_kernel<<<pv2_grid_for(n, 256), 256, 0, stream>>>(in2out, koff, n, n_out, nbr_down, nbr_up);
-  PV2_LAUNCH_OK();
-  return 0;
+  PV2_DONE(n_out > 0 ? 2 : 1);
 }
 
 int pv2_make_indices(const int64_t* grid_coord, const int64_t* offset, int64_t n, int batch, int32_t* indices, void* stream_) {
@@ -355,8 +352,7 @@ int pv2_make_indices(const int64_t* grid_coord, const int64_t* offset, int64_t n
   if (n == 0) return 0;
   PV2_CHECK_ARG(grid_coord && offset && indices && ((uintptr_t)indices & 15) == 0);
   make_indices_kernel<<<pv2_grid_for(n, 256), 256, 0, (cudaStream_t)stream_>>>(grid_coord, offset, n, batch, (int4*)indices);
-  PV2_LAUNCH_OK();
-  return 0;
+  PV2_DONE(1);
 }
 
 }  // extern "C"

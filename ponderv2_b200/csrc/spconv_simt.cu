@@ -209,8 +209,7 @@ int pv2_spconv_gather_gemm_simt(const void* x, const void* w, int64_t w_sco, int
     gather_gemm_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)w, w_sco, w_sk, bias, nbr, (__nv_bfloat16*)y, n_out, cin, cout, kvol);
   else
     return PV2_EUNSUPPORTED;
-  PV2_LAUNCH_OK();
-  return 0;
+  PV2_DONE(1);
 }
 
 int pv2_spconv_wgrad_simt(const void* x, const void* dy, const int32_t* nbr, float* dw, int64_t n_in, int64_t n_out,
@@ -235,8 +234,7 @@ int pv2_spconv_wgrad_simt(const void* x, const void* dy, const int32_t* nbr, flo
     wgrad_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, nbr, dw, n_out, cin, cout, kvol, rows_per_chunk, ci_tiles);
   else
     return PV2_EUNSUPPORTED;
-  PV2_LAUNCH_OK();
-  return 0;
+  PV2_DONE(1);
 }
 
 }  // extern "C"

@@ -132,15 +132,11 @@ __global__ void __launch_bounds__(256) trilinear_bwd_kernel(const S* __restrict_
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     const int64_t n = idx / P, pp = idx - n * P;
     PointCtx<S> p = make_point<S>(grid, idx, D, H, W, pad, align, smooth);
-    S wgt[8], dwx[8], dwy[8], dwz[8];
+    // Same evaluation order as torch's grid_sampler_3d backward (which the reference kernel copies): signed sums of
+    // v * w_b * w_c * gOut per corner, scaled once at the end by the coordinate multiplier (and smoothstep').
+    S wgt[8];
 #pragma unroll
-    for (int s = 0; s < 8; ++s) {
-      int px = s & 1, py = (s >> 1) & 1, pz = (s >> 2) & 1;
-      wgt[s] = p.ax.w[px] * p.ay.w[py] * p.az.w[pz];
-      dwx[s] = p.ax.d[px] * p.ay.w[py] * p.az.w[pz];
-      dwy[s] = p.ax.w[px] * p.ay.d[py] * p.az.w[pz];
-      dwz[s] = p.ax.w[px] * p.ay.w[py] * p.az.d[pz];
-    }
+    for (int s = 0; s < 8; ++s) wgt[s] = p.ax.w[s & 1] * p.ay.w[(s >> 1) & 1] * p.az.w[(s >> 2) & 1];
     S gx = (S)0, gy = (S)0, gz = (S)0;
     const S* in_c = input + n * C * vol;
     const S* go_c = grad_output + n * C * P + pp;
@@ -150,14 +146,21 @@ __global__ void __launch_bounds__(256) trilinear_bwd_kernel(const S* __restrict_
 #pragma unroll
       for (int s = 0; s < 8; ++s) {
         if (p.off[s] < 0) continue;
+        const int px = s & 1, py = (s >> 1) & 1, pz = (s >> 2) & 1;
         const S v = __ldg(in_c + p.off[s]);
-        gx += v * go * dwx[s];
-        gy += v * go * dwy[s];
-        gz += v * go * dwz[s];
+        const S tx = v * p.ay.w[py] * p.az.w[pz] * go;
+        const S ty = v * p.ax.w[px] * p.az.w[pz] * go;
+        const S tz = v * p.ax.w[px] * p.ay.w[py] * go;
+        gx = px ? gx + tx : gx - tx;
+        gy = py ? gy + ty : gy - ty;
+        gz = pz ? gz + tz : gz - tz;
         if (gi_c) atomicAdd(gi_c + p.off[s], go * wgt[s]);
       }
       if (gi_c) gi_c += vol;
     }
+    gx *= p.ax.d[1];
+    gy *= p.ay.d[1];
+    gz *= p.az.d[1];
     grad_grid[idx * 3 + 0] = gx;
     grad_grid[idx * 3 + 1] = gy;
     grad_grid[idx * 3 + 2] = gz;
@@ -247,8 +250,7 @@ int pv2_trilinear_fwd(const void* input, const void* grid, void* output, int64_t
     trilinear_fwd_kernel<double><<<g, 256, 0, stream>>>((const double*)input, (const double*)grid, (double*)output, N, C, (int)D, (int)H, (int)W, P, pad, align != 0, smooth != 0);
   else
     return PV2_EUNSUPPORTED;
-  PV2_LAUNCH_OK();
-  return 0;
+  PV2_DONE(1);
 }
 
 int pv2_trilinear_bwd(const void* grad_output, const void* input, const void* grid, void* grad_input, void* grad_grid,
@@ -265,8 +267,7 @@ int pv2_trilinear_bwd(const void* grad_output, const void* input, const void* gr
     trilinear_bwd_kernel<double><<<g, 256, 0, stream>>>((const double*)grad_output, (const double*)input, (const double*)grid, (double*)grad_input, (double*)grad_grid, N, C, (int)D, (int)H, (int)W, P, pad, align != 0, smooth != 0);
   else
     return PV2_EUNSUPPORTED;
-  PV2_LAUNCH_OK();
-  return 0;
+  PV2_DONE(1);
 }
 
 int pv2_trilinear_bwd_bwd(const void* g_out_input, const void* g_out_grid, const void* input, const void* grid,
@@ -284,8 +285,7 @@ int pv2_trilinear_bwd_bwd(const void* g_out_input, const void* g_out_grid, const
     trilinear_bwd_bwd_kernel<double><<<g, 256, 0, stream>>>((const double*)g_out_input, (const double*)g_out_grid, (const double*)input, (const double*)grid, (const double*)grad_output, (double*)grad_input, (double*)grad_grid, (double*)grad_grad_out, N, C, (int)D, (int)H, (int)W, P, pad, align != 0, smooth != 0);
   else
     return PV2_EUNSUPPORTED;
-  PV2_LAUNCH_OK();
-  return 0;
+  PV2_DONE(1);
 }
 
 }  // extern "C"

@@ -121,7 +121,10 @@ def _gather_gemm(x: torch.Tensor, w3: torch.Tensor, bias: Optional[torch.Tensor]
     assert w3.stride(2) == 1
     x = x.contiguous()
     y = torch.empty((n_out, cout), dtype=x.dtype, device=x.device)
-    with torch.cuda.device(x.device):
+    b = x.element_size()
+    # algorithmic bytes: read X once, write Y once, the weights, the int32 neighbour map
+    nbytes = x.shape[0] * cin * b + n_out * cout * b + kvol * cin * cout * b + 4 * kvol * n_out
+    with torch.cuda.device(x.device), _lib.timed("pv2_spconv_gather_gemm", nbytes, 0):
         _lib.check(lib.pv2_spconv_gather_gemm(_lib.ptr(x), _lib.C.c_void_p(w3.data_ptr()), w3.stride(0), w3.stride(1),
                                               _lib.ptr(bias), _lib.ptr(nbr), _lib.ptr(y), x.shape[0], n_out, cin,
                                               cout, kvol, _lib.dtype_code(x.dtype), _lib.stream_ptr()),
@@ -133,7 +136,9 @@ def _wgrad(x: torch.Tensor, dy: torch.Tensor, nbr: torch.Tensor, kvol: int) -> t
     lib = _lib.load()
     cin, cout = x.shape[1], dy.shape[1]
     dw = torch.zeros((cout, kvol, cin), dtype=torch.float32, device=x.device)
-    with torch.cuda.device(x.device):
+    b = x.element_size()
+    nbytes = x.shape[0] * cin * b + dy.shape[0] * cout * b + kvol * cin * cout * 4 + 4 * kvol * dy.shape[0]
+    with torch.cuda.device(x.device), _lib.timed("pv2_spconv_wgrad", nbytes, 0):
         _lib.check(lib.pv2_spconv_wgrad(_lib.ptr(x.contiguous()), _lib.ptr(dy.contiguous()), _lib.ptr(nbr),
                                         _lib.ptr(dw), x.shape[0], dy.shape[0], cin, cout, kvol,
                                         _lib.dtype_code(x.dtype), _lib.stream_ptr()), "pv2_spconv_wgrad")

@@ -247,7 +247,7 @@ def test_densify_indoor_and_outdoor(cuda_lib):
     grid_shape, grid_size = (16, 16, 8), 0.02
     res = torch.tensor([int(a["grid_coord"].max()), int(b["grid_coord"].max())])
     ref_in = feat.clone().double().requires_grad_(True)
-    ref = do.to_dense_indoor(coord.double(), ref_in, offset, res, grid_shape, grid_size)
+    ref = do.to_dense_indoor(coord, ref_in, offset, res, grid_shape, grid_size)  # coord stays fp32 as in the reference
     batch = torch.from_numpy(so.offset2batch(offset)).to(dev)
     f = feat.to(dev).requires_grad_(True)
     cell = densify.indoor_cells(coord.to(dev), batch, res, grid_shape, grid_size)
