@@ -90,7 +90,10 @@ int pv2_make_indices(const int64_t* grid_coord, const int64_t* offset, int64_t n
 int pv2_spconv_gather_gemm(const void* x, const void* w, int64_t w_stride_co, int64_t w_stride_k,
                            const float* bias, const int32_t* nbr, void* y,
                            int64_t n_in, int64_t n_out, int cin, int cout, int kvol,
-                           int dtype, void* stream);
+                           int dtype, void* workspace, size_t workspace_bytes, void* stream);
+/* Scratch for the fp32 tensor-core path (3xTF32 needs hi/lo split copies of x and w); 0 for bf16.  A call with
+ * less workspace than this still succeeds on the exact-fp32 SIMT kernel. */
+size_t pv2_spconv_workspace_bytes(int64_t n_in, int cin, int cout, int kvol, int dtype);
 
 /* dw[co, k, ci] (+)= sum_j dy[j, co] * x[nbr[k][j], ci];  dw is float32 [Cout, K, Cin], must be
  * zeroed by the caller (accumulated with atomics across row chunks). */

@@ -29,7 +29,9 @@ SIGNATURES = {
     "pv2_rulebook_down": (_int, [_vp, _i64, C.POINTER(C.c_int32), _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pv2_rulebook_down_maps": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp]),
     "pv2_make_indices": (_int, [_vp, _vp, _i64, _int, _vp, _vp]),
-    "pv2_spconv_gather_gemm": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _i64, _int, _int, _int, _int, _vp]),
+    "pv2_spconv_gather_gemm": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _i64, _int, _int, _int, _int, _vp,
+                                       _sz, _vp]),
+    "pv2_spconv_workspace_bytes": (_sz, [_i64, _int, _int, _int, _int]),
     "pv2_spconv_wgrad": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _int, _int, _int, _int, _vp]),
     "pv2_densify_fwd": (_int, [_vp, _vp, _i64, _int, _i64, _vp, _vp, _vp]),
     "pv2_densify_bwd": (_int, [_vp, _vp, _vp, _i64, _int, _vp, _vp]),

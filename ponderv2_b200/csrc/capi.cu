@@ -1,5 +1,6 @@
 // Library-level entry points and the dispatcher between the tensor-core and SIMT sparse-conv kernels.
 #include "pv2_common.cuh"
+#include <stdlib.h>
 
 extern "C" {
 
@@ -10,6 +11,15 @@ int pv2_spconv_wgrad_simt(const void*, const void*, const int32_t*, float*, int6
 static unsigned long long g_launches = 0;
 void pv2_note_launches(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
 int64_t pv2_launch_count(void) { return (int64_t)__atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
+int pv2_spconv_gather_gemm_umma(const void*, const void*, int64_t, int64_t, const float*, const int32_t*, void*, int64_t,
+                                int64_t, int, int, int, int, void*, size_t, void*);
+
+static int force_simt() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("PV2_FORCE_SIMT"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v;
+}
 
 int pv2_version(void) { return 100; }
 
@@ -31,7 +41,14 @@ int pv2_sm_count(void) {
 
 int pv2_spconv_gather_gemm(const void* x, const void* w, int64_t w_sco, int64_t w_sk, const float* bias,
                            const int32_t* nbr, void* y, int64_t n_in, int64_t n_out, int cin, int cout, int kvol,
-                           int dtype, void* stream) {
+                           int dtype, void* workspace, size_t workspace_bytes, void* stream) {
+  // tensor-core implicit GEMM whenever the shape allows it (16-byte aligned channel runs, Cout <= 256, K <= 32);
+  // the ragged stem (Cin = 6 / 4, K = 125) runs on the exact-fp32 SIMT kernel.  PV2_FORCE_SIMT=1 is for A/B tests.
+  if (!force_simt() && (int64_t)cin * kvol >= 64) {
+    int rc = pv2_spconv_gather_gemm_umma(x, w, w_sco, w_sk, bias, nbr, y, n_in, n_out, cin, cout, kvol, dtype, workspace,
+                                         workspace_bytes, stream);
+    if (rc != PV2_EUNSUPPORTED && rc != PV2_EWORKSPACE) return rc;
+  }
   return pv2_spconv_gather_gemm_simt(x, w, w_sco, w_sk, bias, nbr, y, n_in, n_out, cin, cout, kvol, dtype, stream);
 }
 

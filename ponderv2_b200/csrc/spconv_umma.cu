@@ -1,0 +1,414 @@
+// Sparse convolution as an output-stationary implicit GEMM on the Blackwell tensor cores (tcgen05 + TMEM).
+//
+//   Y[j, :] = bias + sum_k W_k . X[nbr[k][j], :]        (SubMConv3d / SparseConv3d / SparseInverseConv3d fwd + dgrad;
+//                                                         reference call sites spconv_unet_v1m1_base.py:47-66,135-177)
+//
+// One CTA owns a tile of 128 output rows and all Cout (<= 256) columns.  The contraction runs over the concatenated
+// axis (kernel offset k, input channel ci) in chunks of 128 bytes per row:
+//   * warps 0-3 (128 threads) gather the A chunk — for output row r the 128 B come from X[nbr[k][row0+r]] (zero-filled
+//     when the neighbour is missing) — and the matching W chunk straight into the 128B-swizzled K-major layout
+//     tcgen05.mma consumes; bf16 uses cp.async (LDGSTS) with zfill, fp32 splits every value into two TF32 halves
+//     (3xTF32: hi*hi + lo*hi + hi*lo, ~2^-21 relative error, i.e. fp32-grade results from the tensor pipe);
+//   * warp 4 issues tcgen05.mma (M = 128, N = Cout padded to 16) into a TMEM accumulator, releasing smem stages with
+//     tcgen05.commit -> mbarrier;
+//   * warps 0-3 then drain TMEM (tcgen05.ld 32x32b), add the bias and write every output row exactly once (no atomics).
+// (tile, offset) pairs with no neighbour at all are skipped by both sides.
+//
+// HBM-side algorithmic bytes per call: N*Cin*b + N*Cout*b + K*Cin*Cout*b + 4*K*N; the gather itself is served by the
+// 126 MB L2 (a feature matrix of 100 k x 96 bf16 is 19 MB).
+#include "pv2_common.cuh"
+#include "umma.cuh"
+
+namespace {
+
+using namespace pv2;
+
+constexpr int kTileM = 128;
+constexpr int kProducerThreads = 128;
+constexpr int kThreads = 160;
+constexpr int kABytes = kTileM * 128;  // one operand tile: 128 rows x 128 B
+constexpr int kMaxStages = 6;
+
+struct GGParams {
+  const void* x;
+  const void* w;
+  int64_t w_sco, w_sk;
+  const float* bias;
+  const int32_t* nbr;
+  void* y;
+  int64_t n_out;
+  int cin, cout, kvol;
+  int n_pad;       // cout rounded up to 16
+  int num_chunks;  // ceil(kvol * cin / elems_per_row)
+  int stages;
+  uint32_t tmem_cols;
+  int64_t x_row;     // elements between consecutive rows of x (2*cin for the split-precision format)
+  int64_t w_lo_off;  // element offset from the hi plane of w to its lo plane (split-precision format)
+  long long* trace;  // development only: per-chunk clock64 stamps of CTA 0 (nullptr in production)
+};
+
+long long* g_trace_ptr = nullptr;
+#define PV2_TRACE(slot, it) do { if (p.trace != nullptr && blockIdx.x == 0 && (it) < 256) p.trace[(it) * 8 + (slot)] = clock64(); } while (0)
+
+template <bool kSplit>
+struct ModeTraits;
+template <>
+struct ModeTraits<false> {  // bf16 storage, kind::f16
+  static constexpr int kEltBytes = 2, kEPR = 64, kEPP = 8, kFmt = 1, kOperands = 1;
+  using Elt = __nv_bfloat16;
+};
+template <>
+struct ModeTraits<true> {  // fp32 storage, 3xTF32
+  static constexpr int kEltBytes = 4, kEPR = 32, kEPP = 4, kFmt = 2, kOperands = 2;
+  using Elt = float;
+};
+
+// v = hi + lo + O(2^-24 |v|): both halves rounded to nearest TF32 (10-bit mantissa), so the tensor core sees exact inputs
+__device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
+  uint32_t h, l;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
+  hi = __uint_as_float(h);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(v - hi));
+  lo = __uint_as_float(l);
+}
+
+// Split-precision storage for the 3xTF32 path.  rows x cols fp32 -> out[row][0][cols] = hi, out[row][1][cols] = lo when
+// `interleave` (activations: one gather fetches both halves), else two planes out[0][...] = hi, out[1][...] = lo (weights).
+__global__ void split_tf32_kernel(const float4* __restrict__ in, float4* __restrict__ out, int64_t rows, int cols4,
+                                  int interleave) {
+  const int64_t total = rows * cols4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(&in[i]);
+    float4 h, l;
+    split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+    if (interleave) {
+      const int64_t r = i / cols4;
+      const int c = (int)(i - r * cols4);
+      out[(r * 2) * cols4 + c] = h;
+      out[(r * 2 + 1) * cols4 + c] = l;
+    } else {
+      out[i] = h;
+      out[total + i] = l;
+    }
+  }
+}
+
+template <bool kSplit>
+__global__ void __launch_bounds__(kThreads) umma_gather_gemm_kernel(const GGParams p) {
+  using T = ModeTraits<kSplit>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // dynamic smem is only guaranteed 16 B aligned: round up to 1024 (the launch reserves the slack)
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const int64_t row0 = (int64_t)blockIdx.x * kTileM;
+
+  const int b_bytes = p.n_pad * 128;
+  const int stage_bytes = (kABytes + b_bytes) * T::kOperands;
+  uint8_t* stage_base = smem;
+  int32_t* idx_s = reinterpret_cast<int32_t*>(smem + (size_t)p.stages * stage_bytes);
+  uint16_t* active = reinterpret_cast<uint16_t*>(idx_s + p.kvol * kTileM);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(
+      (reinterpret_cast<uintptr_t>(active + p.num_chunks) + 7) & ~uintptr_t(7));
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kMaxStages;
+  uint64_t* tmem_full_bar = bars + 2 * kMaxStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 1);
+  uint32_t* kmask_s = tmem_slot + 1;
+  int* n_active_s = reinterpret_cast<int*>(tmem_slot + 2);
+
+  // ---- setup ---------------------------------------------------------------------------------------------
+  for (int i = tid; i < p.kvol * kTileM; i += kThreads) {
+    int k = i / kTileM, r = i - k * kTileM;
+    int64_t j = row0 + r;
+    idx_s[i] = (j < p.n_out) ? __ldg(&p.nbr[(int64_t)k * p.n_out + j]) : -1;
+  }
+  if (tid == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), kProducerThreads);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    mbar_init(smem_u32(tmem_full_bar), 1);
+    *kmask_s = 0;
+    fence_mbar_init();
+  }
+  if (warp == 4) tmem_alloc(smem_u32(tmem_slot), p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // which kernel offsets have at least one neighbour in this tile
+  if (warp < 4) {
+    uint32_t m = 0;
+    for (int k = 0; k < p.kvol; ++k) {
+      unsigned b = __ballot_sync(0xffffffffu, idx_s[k * kTileM + tid] >= 0);
+      if (b) m |= 1u << k;
+    }
+    if (lane == 0 && m) atomicOr(kmask_s, m);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const uint32_t km = *kmask_s;
+    int n = 0;
+    for (int c = 0; c < p.num_chunks; ++c) {
+      int k_lo = (c * T::kEPR) / p.cin;
+      int k_hi = ((c + 1) * T::kEPR - 1) / p.cin;
+      if (k_hi >= p.kvol) k_hi = p.kvol - 1;
+      bool on = false;
+      for (int k = k_lo; k <= k_hi; ++k) on |= ((km >> k) & 1u) != 0;
+      if (on) active[n++] = (uint16_t)c;
+    }
+    // Every CTA streams the same weight chunks; starting each tile at a different chunk spreads the L2 slices the
+    // co-resident CTAs hit at any instant (the order of accumulation is irrelevant to the sum).
+    if (n > 1) {
+      const int rot = (int)((blockIdx.x * 11u) % (unsigned)n);
+      for (int a = 0, b = rot - 1; a < b; ++a, --b) { uint16_t t = active[a]; active[a] = active[b]; active[b] = t; }
+      for (int a = rot, b = n - 1; a < b; ++a, --b) { uint16_t t = active[a]; active[a] = active[b]; active[b] = t; }
+      for (int a = 0, b = n - 1; a < b; ++a, --b) { uint16_t t = active[a]; active[a] = active[b]; active[b] = t; }
+    }
+    *n_active_s = n;
+  }
+  __syncthreads();
+  const int n_active = *n_active_s;
+  const int ktot = p.kvol * p.cin;
+
+  if (warp < 4) {
+    // ======================= producers =======================
+    const int piece = tid & 7;
+    const int rbase = tid >> 3;  // 0..15
+    using E = typename T::Elt;
+    const E* x = reinterpret_cast<const E*>(p.x);
+    const E* w = reinterpret_cast<const E*>(p.w);
+    const int lag = p.stages - 1;
+    const uint32_t tile_off = sw128_offset(rbase, piece);
+    for (int it = 0; it < n_active + lag; ++it) {
+      if (it < n_active) {
+        const int c = active[it];
+        const int s = it % p.stages;
+        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+        if (tid == 0) PV2_TRACE(0, it);
+        mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+        if (tid == 0) PV2_TRACE(1, it);
+        uint8_t* a_tile = stage_base + (size_t)s * stage_bytes;
+        uint8_t* b_tile = a_tile + kABytes * T::kOperands;
+        const int e0 = c * T::kEPR + piece * T::kEPP;
+        const bool kvalid = e0 < ktot;
+        const int k = kvalid ? e0 / p.cin : 0;
+        const int ci = kvalid ? e0 - k * p.cin : 0;
+        const int32_t* idx_k = idx_s + k * kTileM;
+        // all index loads first (independent LDS), then the copies back to back; row r = rbase + 16 i keeps r & 7, so
+        // the swizzled destination advances by a constant 2048 B per i
+        int32_t src[kTileM / 16];
+#pragma unroll
+        for (int i = 0; i < kTileM / 16; ++i) src[i] = kvalid ? idx_k[rbase + 16 * i] : -1;
+        const uint32_t a_dst = smem_u32(a_tile) + tile_off;
+#pragma unroll
+        for (int i = 0; i < kTileM / 16; ++i) {
+          const E* g = (src[i] >= 0) ? x + ((int64_t)src[i] * p.x_row + ci) : x;
+          const uint32_t nb = src[i] >= 0 ? 16u : 0u;
+          cp_async_16(a_dst + i * 2048, g, nb);
+          if constexpr (kSplit) cp_async_16(a_dst + i * 2048 + kABytes, g + p.cin, nb);  // lo half of the row
+        }
+        const uint32_t b_dst = smem_u32(b_tile) + tile_off;
+        const E* wk = w + ((int64_t)k * p.w_sk + ci);
+        for (int n = rbase, i = 0; n < p.n_pad; n += 16, ++i) {
+          const bool ok = kvalid && n < p.cout;
+          const E* g = ok ? wk + (int64_t)n * p.w_sco : w;
+          const uint32_t nb = ok ? 16u : 0u;
+          cp_async_16(b_dst + i * 2048, g, nb);
+          if constexpr (kSplit) cp_async_16(b_dst + i * 2048 + b_bytes, ok ? g + p.w_lo_off : w, nb);
+        }
+      }
+      cp_async_commit();
+      if (tid == 0 && it < n_active) PV2_TRACE(2, it);
+      if (it >= lag) {
+        // chunk (it - lag) has landed for this thread: make it visible to the async proxy and signal
+        switch (lag) {  // wait_group needs an immediate
+          case 1: cp_async_wait<1>(); break;
+          case 2: cp_async_wait<2>(); break;
+          case 3: cp_async_wait<3>(); break;
+          case 4: cp_async_wait<4>(); break;
+          default: cp_async_wait<5>(); break;
+        }
+        if (tid == 0) PV2_TRACE(3, it - lag);
+        fence_proxy_async_smem();
+        mbar_arrive(smem_u32(&full_bar[(it - lag) % p.stages]));
+        if (tid == 0) PV2_TRACE(4, it - lag);
+      }
+    }
+
+    // ======================= epilogue =======================
+    if (n_active > 0) {
+      mbar_wait(smem_u32(tmem_full_bar), 0);
+      tc_fence_after();
+    }
+    const int64_t j = row0 + warp * 32 + lane;
+    const bool row_ok = j < p.n_out;
+    for (int col0 = 0; col0 < p.n_pad; col0 += 16) {
+      uint32_t v[16];
+      if (n_active > 0) {
+        tmem_ld_x16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)col0, v);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = 0u;
+      }
+      if (!row_ok) continue;
+      float f[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int co = col0 + i;
+        f[i] = __uint_as_float(v[i]) + ((p.bias != nullptr && co < p.cout) ? __ldg(&p.bias[co]) : 0.f);
+      }
+      if constexpr (kSplit) {
+        float* yr = reinterpret_cast<float*>(p.y) + j * p.cout + col0;
+        if (col0 + 16 <= p.cout && (p.cout & 3) == 0) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<float4*>(yr + 4 * q) = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+        } else {
+          for (int i = 0; i < 16 && col0 + i < p.cout; ++i) yr[i] = f[i];
+        }
+      } else {
+        __nv_bfloat16* yr = reinterpret_cast<__nv_bfloat16*>(p.y) + j * p.cout + col0;
+        if (col0 + 16 <= p.cout && (p.cout & 7) == 0) {
+          uint32_t pk[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * q], f[2 * q + 1]);
+            pk[q] = *reinterpret_cast<uint32_t*>(&h2);
+          }
+          *reinterpret_cast<uint4*>(yr) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(yr + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        } else {
+          for (int i = 0; i < 16 && col0 + i < p.cout; ++i) yr[i] = __float2bfloat16(f[i]);
+        }
+      }
+    }
+    tc_fence_before();
+  } else {
+    // ======================= MMA issuer (warp 4) =======================
+    const uint32_t idesc = make_idesc(T::kFmt, kTileM, p.n_pad);
+    for (int it = 0; it < n_active; ++it) {
+      const int s = it % p.stages;
+      const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+      if (lane == 0) PV2_TRACE(5, it);
+      mbar_wait(smem_u32(&full_bar[s]), ph);
+      tc_fence_after();
+      if (lane == 0) PV2_TRACE(6, it);
+      if (lane == 0) {
+        // descriptors differ between k-steps only in the start-address field (16-byte units): +2 per 32 B
+        const uint64_t da = smem_desc_kmajor_sw128(smem_u32(stage_base + (size_t)s * stage_bytes));
+        if constexpr (!kSplit) {
+          const uint64_t db = da + (uint64_t)(kABytes >> 4);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) umma_bf16(tmem_base, da + 2 * ks, db + 2 * ks, idesc, (it | ks) != 0 ? 1u : 0u);
+        } else {
+          const uint64_t dal = da + (uint64_t)(kABytes >> 4), dbh = dal + (uint64_t)(kABytes >> 4);
+          const uint64_t dbl = dbh + (uint64_t)(b_bytes >> 4);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            umma_tf32(tmem_base, dal + 2 * ks, dbh + 2 * ks, idesc, (it | ks) != 0 ? 1u : 0u);
+            umma_tf32(tmem_base, da + 2 * ks, dbl + 2 * ks, idesc, 1u);
+            umma_tf32(tmem_base, da + 2 * ks, dbh + 2 * ks, idesc, 1u);
+          }
+        }
+        umma_commit(smem_u32(&empty_bar[s]));               // smem stage reusable once these MMAs retire
+        if (it == n_active - 1) umma_commit(smem_u32(tmem_full_bar));  // accumulator complete
+        PV2_TRACE(7, it);
+      }
+      __syncwarp();
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+template <bool kSplit>
+int launch(const GGParams& p0, cudaStream_t stream) {
+  using T = ModeTraits<kSplit>;
+  GGParams p = p0;
+  p.trace = g_trace_ptr;
+  p.n_pad = (p.cout + 15) / 16 * 16;
+  p.num_chunks = (p.kvol * p.cin + T::kEPR - 1) / T::kEPR;
+  p.tmem_cols = 32;
+  while ((int)p.tmem_cols < p.n_pad) p.tmem_cols <<= 1;
+  const int stage_bytes = (kABytes + p.n_pad * 128) * T::kOperands;
+  const int fixed = p.kvol * kTileM * 4 + p.num_chunks * 2 + 8 + (2 * kMaxStages + 1) * 8 + 64 + 1024;
+  // prefer two resident CTAs per SM (one's epilogue overlaps the other's main loop); fall back to one big CTA
+  int budget = 110 * 1024 - fixed;
+  int stages = budget / stage_bytes;
+  if (stages < 3) { budget = 220 * 1024 - fixed; stages = budget / stage_bytes; }
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) return PV2_EUNSUPPORTED;
+  p.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + fixed;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(umma_gather_gemm_kernel<kSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         227 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  const unsigned grid = (unsigned)((p.n_out + kTileM - 1) / kTileM);
+  umma_gather_gemm_kernel<kSplit><<<grid, kThreads, smem, stream>>>(p);
+  PV2_DONE(1);
+}
+
+}  // namespace
+
+extern "C" {
+
+// development hook: device buffer (>= 2048 int64) receiving CTA 0's per-chunk clock stamps; NULL disables
+void pv2_debug_set_trace(long long* ptr) { g_trace_ptr = ptr; }
+
+// bytes of workspace the fp32 (3xTF32) path needs for the split-precision copies of x and w
+size_t pv2_spconv_workspace_bytes(int64_t n_in, int cin, int cout, int kvol, int dtype) {
+  if (dtype != PV2_F32 || n_in < 0) return 0;
+  size_t xs = ((size_t)n_in * cin * 2 * 4 + 255) / 256 * 256;
+  size_t ws = ((size_t)cout * kvol * cin * 2 * 4 + 255) / 256 * 256;
+  return xs + ws;
+}
+
+// returns PV2_EUNSUPPORTED when the shape does not fit the tensor-core kernel (caller falls back to the SIMT kernel)
+int pv2_spconv_gather_gemm_umma(const void* x, const void* w, int64_t w_sco, int64_t w_sk, const float* bias,
+                                const int32_t* nbr, void* y, int64_t n_in, int64_t n_out, int cin, int cout, int kvol,
+                                int dtype, void* workspace, size_t workspace_bytes, void* stream_) {
+  PV2_CHECK_ARG(n_in >= 0 && n_out >= 0 && cin > 0 && cout > 0 && kvol > 0);
+  if (n_out == 0) return 0;
+  PV2_CHECK_ARG(x && w && nbr && y);
+  const int epp = (dtype == PV2_BF16) ? 8 : 4;
+  if (kvol > 32 || cout > 256 || (cin % epp) != 0 || (w_sco % epp) != 0 || (w_sk % epp) != 0) return PV2_EUNSUPPORTED;
+  if (((uintptr_t)x & 15) || ((uintptr_t)w & 15) || ((uintptr_t)y & 15)) return PV2_EUNSUPPORTED;
+  GGParams p{};
+  p.x = x; p.w = w; p.w_sco = w_sco; p.w_sk = w_sk; p.bias = bias; p.nbr = nbr; p.y = y;
+  p.n_out = n_out; p.cin = cin; p.cout = cout; p.kvol = kvol;
+  p.x_row = cin; p.w_lo_off = 0;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (dtype == PV2_BF16) return launch<false>(p, stream);
+  if (dtype == PV2_F32) {
+    // the weight slab must be one contiguous [cout][kvol][cin] block to be split plane-wise
+    if (w_sk != cin || w_sco != (int64_t)kvol * cin) return PV2_EUNSUPPORTED;
+    const size_t need = pv2_spconv_workspace_bytes(n_in, cin, cout, kvol, dtype);
+    if (workspace == nullptr || workspace_bytes < need || ((uintptr_t)workspace & 15)) return PV2_EWORKSPACE;
+    float* xs = (float*)workspace;
+    float* ws = (float*)((char*)workspace + ((size_t)n_in * cin * 2 * 4 + 255) / 256 * 256);
+    const int64_t welems = (int64_t)cout * kvol * cin;
+    split_tf32_kernel<<<pv2_grid_for(n_in * (cin / 4), 256), 256, 0, stream>>>((const float4*)x, (float4*)xs, n_in, cin / 4, 1);
+    split_tf32_kernel<<<pv2_grid_for(welems / 4, 256), 256, 0, stream>>>((const float4*)w, (float4*)ws, welems / 4, 1, 0);
+    pv2_note_launches(2);
+    p.x = xs; p.x_row = 2 * (int64_t)cin;
+    p.w = ws; p.w_lo_off = welems;
+    return launch<true>(p, stream);
+  }
+  return PV2_EUNSUPPORTED;
+}
+
+}  // extern "C"

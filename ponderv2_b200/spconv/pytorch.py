@@ -124,10 +124,13 @@ def _gather_gemm(x: torch.Tensor, w3: torch.Tensor, bias: Optional[torch.Tensor]
     b = x.element_size()
     # algorithmic bytes: read X once, write Y once, the weights, the int32 neighbour map
     nbytes = x.shape[0] * cin * b + n_out * cout * b + kvol * cin * cout * b + 4 * kvol * n_out
+    dcode = _lib.dtype_code(x.dtype)
+    ws_bytes = lib.pv2_spconv_workspace_bytes(x.shape[0], cin, cout, kvol, dcode)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes else None
     with torch.cuda.device(x.device), _lib.timed("pv2_spconv_gather_gemm", nbytes, 0):
         _lib.check(lib.pv2_spconv_gather_gemm(_lib.ptr(x), _lib.C.c_void_p(w3.data_ptr()), w3.stride(0), w3.stride(1),
                                               _lib.ptr(bias), _lib.ptr(nbr), _lib.ptr(y), x.shape[0], n_out, cin,
-                                              cout, kvol, _lib.dtype_code(x.dtype), _lib.stream_ptr()),
+                                              cout, kvol, dcode, _lib.ptr(ws), ws_bytes, _lib.stream_ptr()),
                    "pv2_spconv_gather_gemm")
     return y
 
