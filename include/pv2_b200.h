@@ -138,6 +138,44 @@ int pv2_trilinear_bwd_bwd(const void* grad_out_input, const void* grad_out_grid,
                           int padding_mode, int align_corners, int apply_smoothstep,
                           int dtype, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Render MLP building block: dense per-row linear layer on the tensor cores (fp32 storage, 3xTF32).
+ * Replaces the nn.Linear chains of ponder/models/ponder/render_utils/decoders.py:6-109.
+ *   y[j, 0:cout] = act(x[j, 0:cin] . w^T + bias);  w is [cout, cin] row-major.
+ * x: plain [rows, cin] (x_presplit = 0, x_row = cin) or split-precision (hi at x[j*x_row + c], lo at +x_lo_off).
+ * y (and y2 when act = 1): row stride y_row; y_split = 1 writes TF32 hi/lo halves (lo at +y_lo_off).
+ * act: 0 none; 1 y = softplus(beta=100, threshold=20), y2 = sigmoid(100 v) (the softplus derivative).
+ * ------------------------------------------------------------------------------------------ */
+size_t pv2_linear_workspace_bytes(int64_t rows, int cin, int cout, int x_presplit);
+int pv2_linear(const float* x, int64_t x_row, int64_t x_lo_off, int x_presplit, const float* w, const float* bias,
+               float* y, int64_t y_row, int64_t y_lo_off, int y_split, int act, float* y2, int64_t y2_row,
+               int64_t y2_lo_off, int64_t rows, int cin, int cout, void* workspace, size_t workspace_bytes,
+               void* stream);
+/* dw[co, ci] += sum_j dy[j, co] * x[j, ci]; operands plain (lo_off = 0) or split-precision (value = hi + lo). */
+int pv2_dense_wgrad(const float* x, int64_t x_row, int64_t x_lo_off, const float* dy, int64_t dy_row,
+                    int64_t dy_lo_off, int64_t rows, int cin, int cout, float* dw, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Renderer field kernels on a channels-last volume [Z][Y][X][C] (fields/sdf_field.py:148-257 and the
+ * sampler kernels smooth_sampler_kernel.cu:39-619 they drive).  pts are normalised coordinates in [0,1]^3
+ * (grid = 2p-1, zeros padding, align_corners=True).
+ * ------------------------------------------------------------------------------------------ */
+/* trilinear fetch of channels [0,c_use): [0,ca) -> out_a split-precision, [ca,c_use) -> out_b plain */
+int pv2_field_sample_fwd(const float* vol, const float* pts, int64_t P, int Z, int Y, int X, int C, int c_use, int ca,
+                         float* out_a, int64_t a_row, int64_t a_lo, float* out_b, int64_t b_row, void* stream);
+/* grad = d sdf/d p = J^T u;  rgb = sigmoid(Mr [grad|f_r|geo|dir] + cr);  Mr is [3,134] */
+int pv2_field_post_fwd(const float* vol, const float* pts, const float* dirs, int samples_per_ray, const float* u,
+                       const float* f_r, const float* out_geo, int64_t geo_row, const float* Mr, const float* cr,
+                       int64_t P, int Z, int Y, int X, int C, float* grad, float* rgb, void* stream);
+int pv2_field_post_bwd(const float* vol, const float* pts, const float* dirs, int samples_per_ray, const float* f_r,
+                       const float* out_geo, int64_t geo_row, const float* grad, const float* rgb, const float* Mr,
+                       const float* g_rgb, const float* g_grad, const float* g_sdf, int64_t P, int Z, int Y, int X,
+                       int C, float* gbar, float* dF, int64_t dF_row, float* doutbar, float* ubar, float* dMr,
+                       float* dcr, void* stream);
+/* dvol[corner,c] += w dF[p,c] + [c<cs] (dw.gbar) u[p,c]   (u may be NULL) */
+int pv2_field_sample_bwd(const float* pts, const float* dF, int64_t dF_row, const float* u, const float* gbar,
+                         int64_t P, int Z, int Y, int X, int C, int cs, float* dvol, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -33,6 +33,16 @@ SIGNATURES = {
                                        _sz, _vp]),
     "pv2_spconv_workspace_bytes": (_sz, [_i64, _int, _int, _int, _int]),
     "pv2_spconv_wgrad": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _int, _int, _int, _int, _vp]),
+    "pv2_linear_workspace_bytes": (_sz, [_i64, _int, _int, _int]),
+    "pv2_linear": (_int, [_vp, _i64, _i64, _int, _vp, _vp, _vp, _i64, _i64, _int, _int, _vp, _i64, _i64, _i64, _int, _int,
+                           _vp, _sz, _vp]),
+    "pv2_dense_wgrad": (_int, [_vp, _i64, _i64, _vp, _i64, _i64, _i64, _int, _int, _vp, _vp]),
+    "pv2_field_sample_fwd": (_int, [_vp, _vp, _i64, _int, _int, _int, _int, _int, _int, _vp, _i64, _i64, _vp, _i64, _vp]),
+    "pv2_field_post_fwd": (_int, [_vp, _vp, _vp, _int, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _int, _int, _int, _int, _vp,
+                                   _vp, _vp]),
+    "pv2_field_post_bwd": (_int, [_vp, _vp, _vp, _int, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _int,
+                                   _int, _int, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "pv2_field_sample_bwd": (_int, [_vp, _vp, _i64, _vp, _vp, _i64, _int, _int, _int, _int, _int, _vp, _vp]),
     "pv2_densify_fwd": (_int, [_vp, _vp, _i64, _int, _i64, _vp, _vp, _vp]),
     "pv2_densify_bwd": (_int, [_vp, _vp, _vp, _i64, _int, _vp, _vp]),
     "pv2_trilinear_fwd": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _int, _int, _int, _int, _vp]),

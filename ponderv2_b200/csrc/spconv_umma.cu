@@ -44,6 +44,13 @@ struct GGParams {
   uint32_t tmem_cols;
   int64_t x_row;     // elements between consecutive rows of x (2*cin for the split-precision format)
   int64_t w_lo_off;  // element offset from the hi plane of w to its lo plane (split-precision format)
+  int64_t x_lo_off;  // element offset from the hi half of an x row to its lo half (split-precision format)
+  // output: row stride, optional split-precision output (hi at y, lo at y + y_lo_off) and the fused epilogue
+  int64_t y_row, y_lo_off;
+  int y_split;       // fp32 only: write TF32 hi/lo halves instead of the plain value
+  int act;           // 0: none; 1: y = softplus(beta=100, threshold=20)(v), y2 = sigmoid(100 v)   (SDF decoder, decoders.py:24)
+  void* y2;
+  int64_t y2_row, y2_lo_off;
   long long* trace;  // development only: per-chunk clock64 stamps of CTA 0 (nullptr in production)
 };
 
@@ -123,7 +130,7 @@ __global__ void __launch_bounds__(kThreads) umma_gather_gemm_kernel(const GGPara
   for (int i = tid; i < p.kvol * kTileM; i += kThreads) {
     int k = i / kTileM, r = i - k * kTileM;
     int64_t j = row0 + r;
-    idx_s[i] = (j < p.n_out) ? __ldg(&p.nbr[(int64_t)k * p.n_out + j]) : -1;
+    idx_s[i] = (j < p.n_out) ? (p.nbr != nullptr ? __ldg(&p.nbr[(int64_t)k * p.n_out + j]) : (int32_t)j) : -1;
   }
   if (tid == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -210,7 +217,7 @@ __global__ void __launch_bounds__(kThreads) umma_gather_gemm_kernel(const GGPara
           const E* g = (src[i] >= 0) ? x + ((int64_t)src[i] * p.x_row + ci) : x;
           const uint32_t nb = src[i] >= 0 ? 16u : 0u;
           cp_async_16(a_dst + i * 2048, g, nb);
-          if constexpr (kSplit) cp_async_16(a_dst + i * 2048 + kABytes, g + p.cin, nb);  // lo half of the row
+          if constexpr (kSplit) cp_async_16(a_dst + i * 2048 + kABytes, g + p.x_lo_off, nb);  // lo half of the row
         }
         const uint32_t b_dst = smem_u32(b_tile) + tile_off;
         const E* wk = w + ((int64_t)k * p.w_sk + ci);
@@ -264,16 +271,45 @@ __global__ void __launch_bounds__(kThreads) umma_gather_gemm_kernel(const GGPara
         f[i] = __uint_as_float(v[i]) + ((p.bias != nullptr && co < p.cout) ? __ldg(&p.bias[co]) : 0.f);
       }
       if constexpr (kSplit) {
-        float* yr = reinterpret_cast<float*>(p.y) + j * p.cout + col0;
-        if (col0 + 16 <= p.cout && (p.cout & 3) == 0) {
+        float g2[16];
+        if (p.act == 1) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
-            *reinterpret_cast<float4*>(yr + 4 * q) = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
-        } else {
-          for (int i = 0; i < 16 && col0 + i < p.cout; ++i) yr[i] = f[i];
+          for (int i = 0; i < 16; ++i) {
+            const float t = 100.f * f[i];
+            g2[i] = 1.f / (1.f + __expf(-t));
+            f[i] = (t > 20.f) ? f[i] : log1pf(expf(t)) * 0.01f;
+          }
         }
+        const bool vec = (col0 + 16 <= p.cout) && ((p.cout & 3) == 0);
+        auto store = [&](float* base, int64_t row_stride, int64_t lo_off, const float (&val)[16], bool split) {
+          float* yr = base + j * row_stride + col0;
+          if (!split) {
+            if (vec) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                *reinterpret_cast<float4*>(yr + 4 * q) = make_float4(val[4 * q], val[4 * q + 1], val[4 * q + 2], val[4 * q + 3]);
+            } else {
+              for (int i = 0; i < 16 && col0 + i < p.cout; ++i) yr[i] = val[i];
+            }
+          } else {
+            float hi[16], lo[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) split_tf32(val[i], hi[i], lo[i]);
+            if (vec) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                *reinterpret_cast<float4*>(yr + 4 * q) = make_float4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+                *reinterpret_cast<float4*>(yr + lo_off + 4 * q) = make_float4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+              }
+            } else {
+              for (int i = 0; i < 16 && col0 + i < p.cout; ++i) { yr[i] = hi[i]; yr[lo_off + i] = lo[i]; }
+            }
+          }
+        };
+        store(reinterpret_cast<float*>(p.y), p.y_row, p.y_lo_off, f, p.y_split != 0);
+        if (p.act == 1 && p.y2 != nullptr) store(reinterpret_cast<float*>(p.y2), p.y2_row, p.y2_lo_off, g2, p.y_split != 0);
       } else {
-        __nv_bfloat16* yr = reinterpret_cast<__nv_bfloat16*>(p.y) + j * p.cout + col0;
+        __nv_bfloat16* yr = reinterpret_cast<__nv_bfloat16*>(p.y) + j * p.y_row + col0;
         if (col0 + 16 <= p.cout && (p.cout & 7) == 0) {
           uint32_t pk[8];
 #pragma unroll
@@ -390,7 +426,8 @@ int pv2_spconv_gather_gemm_umma(const void* x, const void* w, int64_t w_sco, int
   GGParams p{};
   p.x = x; p.w = w; p.w_sco = w_sco; p.w_sk = w_sk; p.bias = bias; p.nbr = nbr; p.y = y;
   p.n_out = n_out; p.cin = cin; p.cout = cout; p.kvol = kvol;
-  p.x_row = cin; p.w_lo_off = 0;
+  p.x_row = cin; p.w_lo_off = 0; p.x_lo_off = 0;
+  p.y_row = cout; p.y_lo_off = 0; p.y_split = 0; p.act = 0; p.y2 = nullptr; p.y2_row = 0; p.y2_lo_off = 0;
   cudaStream_t stream = (cudaStream_t)stream_;
   if (dtype == PV2_BF16) return launch<false>(p, stream);
   if (dtype == PV2_F32) {
@@ -404,11 +441,57 @@ int pv2_spconv_gather_gemm_umma(const void* x, const void* w, int64_t w_sco, int
     split_tf32_kernel<<<pv2_grid_for(n_in * (cin / 4), 256), 256, 0, stream>>>((const float4*)x, (float4*)xs, n_in, cin / 4, 1);
     split_tf32_kernel<<<pv2_grid_for(welems / 4, 256), 256, 0, stream>>>((const float4*)w, (float4*)ws, welems / 4, 1, 0);
     pv2_note_launches(2);
-    p.x = xs; p.x_row = 2 * (int64_t)cin;
+    p.x = xs; p.x_row = 2 * (int64_t)cin; p.x_lo_off = cin;
     p.w = ws; p.w_lo_off = welems;
     return launch<true>(p, stream);
   }
   return PV2_EUNSUPPORTED;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Dense per-row linear layer on the same tensor-core kernel (identity row map): the render MLP (decoders.py:6-109).
+//   y[j, 0:cout] = act( x[j, 0:cin] . w[0:cout, 0:cin]^T + bias )          fp32 storage, 3xTF32 arithmetic
+// x may already be in split-precision form (hi at x[j*x_row + c], lo at x[j*x_row + x_lo_off + c]); otherwise it is
+// split into the workspace first.  y / y2 can be written plain or split (so the next layer needs no split pass).
+size_t pv2_linear_workspace_bytes(int64_t rows, int cin, int cout, int x_presplit) {
+  size_t xs = x_presplit ? 0 : ((size_t)rows * cin * 2 * 4 + 255) / 256 * 256;
+  size_t ws = ((size_t)cout * cin * 2 * 4 + 255) / 256 * 256;
+  return xs + ws;
+}
+
+int pv2_linear(const float* x, int64_t x_row, int64_t x_lo_off, int x_presplit, const float* w, const float* bias,
+               float* y, int64_t y_row, int64_t y_lo_off, int y_split, int act, float* y2, int64_t y2_row,
+               int64_t y2_lo_off, int64_t rows, int cin, int cout, void* workspace, size_t workspace_bytes,
+               void* stream_) {
+  PV2_CHECK_ARG(rows >= 0 && cin > 0 && cout > 0 && cout <= 256 && (cin % 4) == 0 && act >= 0 && act <= 1);
+  if (rows == 0) return 0;
+  PV2_CHECK_ARG(x && w && y && workspace);
+  PV2_CHECK_ARG((x_row % 4) == 0 && (x_lo_off % 4) == 0 && (((uintptr_t)x | (uintptr_t)w | (uintptr_t)y) & 15) == 0);
+  PV2_CHECK_ARG(!x_presplit || x_lo_off > 0);
+  if (workspace_bytes < pv2_linear_workspace_bytes(rows, cin, cout, x_presplit)) return PV2_EWORKSPACE;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  char* wsp = (char*)workspace;
+  GGParams p{};
+  int launches = 1;
+  if (!x_presplit) {
+    PV2_CHECK_ARG(x_row == cin);  // the split pass reads a dense [rows, cin] matrix
+    float* xs = (float*)wsp;
+    wsp += ((size_t)rows * cin * 2 * 4 + 255) / 256 * 256;
+    split_tf32_kernel<<<pv2_grid_for(rows * (cin / 4), 256), 256, 0, stream>>>((const float4*)x, (float4*)xs, rows, cin / 4, 1);
+    p.x = xs; p.x_row = 2 * (int64_t)cin; p.x_lo_off = cin;
+    ++launches;
+  } else {
+    p.x = x; p.x_row = x_row; p.x_lo_off = x_lo_off;
+  }
+  float* wsplit = (float*)wsp;
+  const int64_t welems = (int64_t)cout * cin;
+  split_tf32_kernel<<<pv2_grid_for(welems / 4, 256), 256, 0, stream>>>((const float4*)w, (float4*)wsplit, welems / 4, 1, 0);
+  pv2_note_launches(launches);
+  p.w = wsplit; p.w_sco = cin; p.w_sk = cin; p.w_lo_off = welems;
+  p.bias = bias; p.nbr = nullptr; p.y = y; p.n_out = rows; p.cin = cin; p.cout = cout; p.kvol = 1;
+  p.y_row = y_row; p.y_lo_off = y_lo_off; p.y_split = y_split; p.act = act;
+  p.y2 = y2; p.y2_row = y2_row; p.y2_lo_off = y2_lo_off;
+  return launch<true>(p, stream);
 }
 
 }  // extern "C"

@@ -22,6 +22,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from ..smooth_sampler import SmoothSampler
+from . import fused
 
 
 class RayBundle:
@@ -284,6 +285,9 @@ class NeuSModel(nn.Module):
         self.loss = _LossCfg(loss)
         self.anneal_end = 50000
         self.background_color = (0.0, 0.0, 0.0)
+        # hand-derived tensor-core field (render/fused.py) whenever the configuration is the indoor one; the generic
+        # autograd-through-the-sampler path otherwise.  Both are CUDA-only.
+        self.use_fused = True
 
     def forward(self, ray_bundle: RayBundle, volume_feature: List[torch.Tensor], noise: Optional[dict] = None,
                 **kwargs) -> Dict[str, torch.Tensor]:
@@ -296,6 +300,14 @@ class NeuSModel(nn.Module):
         to_euclid = lambda b: b * fars + (1 - b) * nears
         smp = self.sampler
         R = rb.origins.shape[0]
+        use_fused = (self.use_fused and fused.eligible(self.field) and len(volume_feature) == 1
+                     and volume_feature[0].shape[0] == 128)
+        if use_fused:
+            vol_cl = volume_feature[0].permute(1, 2, 3, 0).contiguous().float()  # free for channels_last_3d volumes
+            fp = fused.fold_parameters(self.field)
+            vol_ng = vol_cl.detach()
+            M0_ng, c0_ng = fp["M0"].detach(), fp["c0"].detach()
+            w4_ng, c4_ng = fp["wcat"][:4].detach().contiguous(), fp["c1"][:4].detach().contiguous()
         bins = smp.uniform_bins(R, rb.origins, noise.get("uniform"))
         starts_sp, end_sp = bins[:, :-1], bins[:, -1:]
         out: Dict[str, torch.Tensor] = {}
@@ -304,7 +316,11 @@ class NeuSModel(nn.Module):
         for it in range(smp.num_upsample_steps):
             with torch.no_grad():
                 new_pts = o3 + d3 * to_euclid(new_sp)[..., None]
-                new_sdf = self.field.get_sdf(new_pts, volume_feature)[0].squeeze(-1)
+                if use_fused:
+                    new_sdf = fused.coarse_sdf(vol_ng, new_pts.reshape(-1, 3), M0_ng, c0_ng, w4_ng, c4_ng).view(
+                        new_pts.shape[:-1])
+                else:
+                    new_sdf = self.field.get_sdf(new_pts, volume_feature)[0].squeeze(-1)
             sdf = new_sdf if sorted_index is None else torch.gather(torch.cat([sdf, new_sdf], -1), 1, sorted_index)
             eu = to_euclid(torch.cat([starts_sp, end_sp], -1))
             alphas = smp.fixed_inv_s_alphas(sdf, eu[:, 1:] - eu[:, :-1], smp.base_variance * 2 ** it)
@@ -324,7 +340,22 @@ class NeuSModel(nn.Module):
         deltas = ends - starts
         pts = o3 + d3 * starts
         dirs = d3.expand(-1, starts.shape[1], -1)
-        fo = self.field(pts, dirs, deltas, volume_feature, return_alphas=True)
+        if use_fused:
+            fld = self.field
+            pn = pts
+            if fld.norm_pts:
+                pn = pn / (1 + fld.norm_padding + 10e-4) + 0.5
+                pn = torch.where(pn >= 1, torch.full_like(pn, 1 - 10e-4), pn)
+                pn = torch.where(pn < 0, torch.zeros_like(pn), pn)
+            S = starts.shape[1]
+            sdf_f, grad_f, rgb_f = fused.FusedFieldFunction.apply(
+                vol_cl, pn.reshape(-1, 3), rb.directions, S, fp["M0"], fp["c0"], fp["wcat"], fp["c1"], fp["wp"],
+                fp["m10"], fp["Mr"], fp["cr"])
+            sdf_f, grad_f = sdf_f.view(R, S, 1), grad_f.view(R, S, 3)
+            fo = dict(sdf=sdf_f, gradients=grad_f, rgb=rgb_f.view(R, S, 3), normal=F.normalize(grad_f, dim=-1),
+                      alphas=fld.get_alpha(dirs, deltas, sdf_f, grad_f))
+        else:
+            fo = self.field(pts, dirs, deltas, volume_feature, return_alphas=True)
         weights = weights_from_alphas(fo["alphas"])
         depth = (weights * starts).sum(-2) / (weights.sum(-2) + 1e-10)
         depth = torch.maximum(torch.minimum(depth, starts.amax()), starts.amin())
