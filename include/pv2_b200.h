@@ -99,7 +99,10 @@ size_t pv2_spconv_workspace_bytes(int64_t n_in, int cin, int cout, int kvol, int
  * zeroed by the caller (accumulated with atomics across row chunks). */
 int pv2_spconv_wgrad(const void* x, const void* dy, const int32_t* nbr, float* dw,
                      int64_t n_in, int64_t n_out, int cin, int cout, int kvol,
-                     int dtype, void* stream);
+                     int dtype, void* workspace, size_t workspace_bytes, void* stream);
+/* scratch of the fp32 tensor-core weight-gradient kernel (split-precision copies of x and dy); without it the
+ * exact-fp32 SIMT kernel runs */
+size_t pv2_wgrad_workspace_bytes(int64_t n_in, int64_t n_out, int cin, int cout);
 
 /* ------------------------------------------------------------------------------------------
  * Densify: voxel features -> dense channels-last volume, scatter-mean
@@ -153,7 +156,8 @@ int pv2_linear(const float* x, int64_t x_row, int64_t x_lo_off, int x_presplit, 
                void* stream);
 /* dw[co, ci] += sum_j dy[j, co] * x[j, ci]; operands plain (lo_off = 0) or split-precision (value = hi + lo). */
 int pv2_dense_wgrad(const float* x, int64_t x_row, int64_t x_lo_off, const float* dy, int64_t dy_row,
-                    int64_t dy_lo_off, int64_t rows, int cin, int cout, float* dw, void* stream);
+                    int64_t dy_lo_off, int64_t rows, int cin, int cout, float* dw, void* workspace,
+                    size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Renderer field kernels on a channels-last volume [Z][Y][X][C] (fields/sdf_field.py:148-257 and the

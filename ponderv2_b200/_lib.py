@@ -32,11 +32,12 @@ SIGNATURES = {
     "pv2_spconv_gather_gemm": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _i64, _int, _int, _int, _int, _vp,
                                        _sz, _vp]),
     "pv2_spconv_workspace_bytes": (_sz, [_i64, _int, _int, _int, _int]),
-    "pv2_spconv_wgrad": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _int, _int, _int, _int, _vp]),
+    "pv2_spconv_wgrad": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _int, _int, _int, _int, _vp, _sz, _vp]),
+    "pv2_wgrad_workspace_bytes": (_sz, [_i64, _i64, _int, _int]),
     "pv2_linear_workspace_bytes": (_sz, [_i64, _int, _int, _int]),
     "pv2_linear": (_int, [_vp, _i64, _i64, _int, _vp, _vp, _vp, _i64, _i64, _int, _int, _vp, _i64, _i64, _i64, _int, _int,
                            _vp, _sz, _vp]),
-    "pv2_dense_wgrad": (_int, [_vp, _i64, _i64, _vp, _i64, _i64, _i64, _int, _int, _vp, _vp]),
+    "pv2_dense_wgrad": (_int, [_vp, _i64, _i64, _vp, _i64, _i64, _i64, _int, _int, _vp, _vp, _sz, _vp]),
     "pv2_field_sample_fwd": (_int, [_vp, _vp, _i64, _int, _int, _int, _int, _int, _int, _vp, _i64, _i64, _vp, _i64, _vp]),
     "pv2_field_post_fwd": (_int, [_vp, _vp, _vp, _int, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _int, _int, _int, _int, _vp,
                                    _vp, _vp]),

@@ -52,8 +52,18 @@ int pv2_spconv_gather_gemm(const void* x, const void* w, int64_t w_sco, int64_t 
   return pv2_spconv_gather_gemm_simt(x, w, w_sco, w_sk, bias, nbr, y, n_in, n_out, cin, cout, kvol, dtype, stream);
 }
 
+int pv2_wgrad_umma(const float*, int64_t, int64_t, const float*, int64_t, int64_t, const int32_t*, float*, int64_t, int64_t,
+                   int, int, int, void*, size_t, void*);
+
 int pv2_spconv_wgrad(const void* x, const void* dy, const int32_t* nbr, float* dw, int64_t n_in, int64_t n_out, int cin,
-                     int cout, int kvol, int dtype, void* stream) {
+                     int cout, int kvol, int dtype, void* workspace, size_t workspace_bytes, void* stream) {
+  // tensor-core wgrad pays off once the gathered rows are wide (measured on B200, 100 k voxels, K = 27:
+  // 96->96 1.6 vs 2.4 ms, 256->256 6.4 vs 10.1 ms, but 32->32 1.1 vs 0.6 ms): narrow layers stay on the SIMT kernel
+  if (!force_simt() && dtype == PV2_F32 && kvol <= 32 && cin >= 96) {
+    int rc = pv2_wgrad_umma((const float*)x, cin, 0, (const float*)dy, cout, 0, nbr, dw, n_in, n_out, cin, cout, kvol,
+                            workspace, workspace_bytes, stream);
+    if (rc != PV2_EUNSUPPORTED && rc != PV2_EWORKSPACE) return rc;
+  }
   return pv2_spconv_wgrad_simt(x, dy, nbr, dw, n_in, n_out, cin, cout, kvol, dtype, stream);
 }
 

@@ -9,6 +9,7 @@
 // All of these are gather/scatter kernels bound by L2/HBM traffic: per point 8*C*4 B of corner rows (<= 4 KB at C=128,
 // ~half of it shared with the neighbouring sample of the same ray) plus the per-point outputs.
 #include "pv2_common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -455,8 +456,20 @@ __global__ void __launch_bounds__(256) dense_wgrad_kernel(const float* __restric
 
 }  // namespace
 
+extern "C" int pv2_wgrad_umma(const float*, int64_t, int64_t, const float*, int64_t, int64_t, const int32_t*, float*,
+                              int64_t, int64_t, int, int, int, void*, size_t, void*);
+
 extern "C" int pv2_dense_wgrad(const float* x, int64_t x_row, int64_t x_lo_off, const float* dy, int64_t dy_row,
-                               int64_t dy_lo_off, int64_t rows, int cin, int cout, float* dw, void* stream_) {
+                               int64_t dy_lo_off, int64_t rows, int cin, int cout, float* dw, void* workspace,
+                               size_t workspace_bytes, void* stream_) {
+  {
+    const char* e = getenv("PV2_FORCE_SIMT");
+    if (!(e && e[0] == '1') && cin >= 96) {
+      int rc = pv2_wgrad_umma(x, x_row, x_lo_off, dy, dy_row, dy_lo_off, nullptr, dw, rows, rows, cin, cout, 1, workspace,
+                              workspace_bytes, stream_);
+      if (rc != PV2_EUNSUPPORTED && rc != PV2_EWORKSPACE) return rc;
+    }
+  }
   PV2_CHECK_ARG(rows >= 0 && cin > 0 && cout > 0);
   if (rows == 0) return 0;
   PV2_CHECK_ARG(x && dy && dw);

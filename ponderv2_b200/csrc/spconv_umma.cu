@@ -51,6 +51,8 @@ struct GGParams {
   int act;           // 0: none; 1: y = softplus(beta=100, threshold=20)(v), y2 = sigmoid(100 v)   (SDF decoder, decoders.py:24)
   void* y2;
   int64_t y2_row, y2_lo_off;
+  int ksplit;        // > 1: gridDim.y CTAs share one row tile, each reduces a slice of the contraction and adds its
+                     // partial result into the (pre-zeroed) output with red.global.add (small deep U-Net levels)
   long long* trace;  // development only: per-chunk clock64 stamps of CTA 0 (nullptr in production)
 };
 
@@ -176,6 +178,15 @@ __global__ void __launch_bounds__(kThreads) umma_gather_gemm_kernel(const GGPara
       for (int a = rot, b = n - 1; a < b; ++a, --b) { uint16_t t = active[a]; active[a] = active[b]; active[b] = t; }
       for (int a = 0, b = n - 1; a < b; ++a, --b) { uint16_t t = active[a]; active[a] = active[b]; active[b] = t; }
     }
+    if (p.ksplit > 1) {  // keep only this CTA's contiguous slice of the active chunks
+      const int per = (n + p.ksplit - 1) / p.ksplit;
+      const int lo = (int)blockIdx.y * per;
+      int hi = lo + per;
+      if (hi > n) hi = n;
+      int m = 0;
+      for (int a = lo; a < hi; ++a) active[m++] = active[a];
+      n = m;
+    }
     *n_active_s = n;
   }
   __syncthreads();
@@ -268,7 +279,7 @@ __global__ void __launch_bounds__(kThreads) umma_gather_gemm_kernel(const GGPara
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const int co = col0 + i;
-        f[i] = __uint_as_float(v[i]) + ((p.bias != nullptr && co < p.cout) ? __ldg(&p.bias[co]) : 0.f);
+        f[i] = __uint_as_float(v[i]) + ((p.bias != nullptr && co < p.cout && blockIdx.y == 0) ? __ldg(&p.bias[co]) : 0.f);
       }
       if constexpr (kSplit) {
         float g2[16];
@@ -281,6 +292,22 @@ __global__ void __launch_bounds__(kThreads) umma_gather_gemm_kernel(const GGPara
           }
         }
         const bool vec = (col0 + 16 <= p.cout) && ((p.cout & 3) == 0);
+        if (p.ksplit > 1) {
+          float* yr = reinterpret_cast<float*>(p.y) + j * p.y_row + col0;
+          if (n_active > 0) {
+            if (vec) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(yr + 4 * q), "f"(f[4 * q]),
+                             "f"(f[4 * q + 1]), "f"(f[4 * q + 2]), "f"(f[4 * q + 3]) : "memory");
+            } else {
+              for (int i = 0; i < 16 && col0 + i < p.cout; ++i) atomicAdd(yr + i, f[i]);
+            }
+          } else if (blockIdx.y == 0 && p.bias != nullptr) {
+            for (int i = 0; i < 16 && col0 + i < p.cout; ++i) atomicAdd(yr + i, f[i]);
+          }
+          continue;
+        }
         auto store = [&](float* base, int64_t row_stride, int64_t lo_off, const float (&val)[16], bool split) {
           float* yr = base + j * row_stride + col0;
           if (!split) {
@@ -393,9 +420,22 @@ int launch(const GGParams& p0, cudaStream_t stream) {
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  const unsigned grid = (unsigned)((p.n_out + kTileM - 1) / kTileM);
+  const unsigned tiles = (unsigned)((p.n_out + kTileM - 1) / kTileM);
+  int ksplit = 1;
+  if (kSplit && !p.y_split && p.act == 0 && tiles * 2 <= PV2_SM_COUNT && p.num_chunks >= 16) {
+    ksplit = (PV2_SM_COUNT + (int)tiles - 1) / (int)tiles;  // ~one CTA per SM in total
+    if (ksplit > p.num_chunks / 8) ksplit = p.num_chunks / 8;
+    if (ksplit < 1) ksplit = 1;
+  }
+  p.ksplit = ksplit;
+  int launches = 1;
+  if (ksplit > 1) {
+    cudaMemsetAsync(p.y, 0, (size_t)p.n_out * p.y_row * sizeof(float), stream);
+    ++launches;
+  }
+  dim3 grid(tiles, (unsigned)ksplit);
   umma_gather_gemm_kernel<kSplit><<<grid, kThreads, smem, stream>>>(p);
-  PV2_DONE(1);
+  PV2_DONE(launches);
 }
 
 }  // namespace

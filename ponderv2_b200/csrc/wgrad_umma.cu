@@ -1,0 +1,317 @@
+// Weight gradient of the sparse convolutions (and of the render MLP's dense layers) on the Blackwell tensor cores.
+//
+//   dW[co, k, ci] += sum_j dY[j, co] * X[nbr[k][j], ci]            (wgrad of SubMConv3d / SparseConv3d / Inverse)
+//
+// This is a GEMM whose contraction runs over the voxel rows j.  tcgen05's TF32 path takes K-major operands only
+// (measured: setting the MN-major bits of the instruction descriptor with kind::tf32 yields an all-zero accumulator),
+// so both operands are brought into K-major form, i.e. "channel x 32 consecutive rows" tiles:
+//   * A = dY^T: a small transposing split kernel writes dY once as [2 (hi|lo)][Cout][N] and the tile rows are then
+//     plain 128-byte runs copied with cp.async;
+//   * B = X[nbr[k][j]]^T: gathered rows cannot be pre-transposed (a different permutation per offset k), so each lane
+//     owns one row j, reads its channels with 128-bit loads, splits them into TF32 hi/lo and writes them as a column of
+//     the swizzled tile — lanes of a warp hit 32 different banks, so the transposing stores are conflict-free.
+// One CTA owns (row chunk, kernel offset k, 128-wide slice of Cout), accumulates its partial dW_k in TMEM
+// (128 lanes = output channels, Cin columns) over all its rows with 3xTF32 arithmetic (hi*hi + lo*hi + hi*lo) and
+// finally adds it into dW with 128-bit vector reductions.
+#include "pv2_common.cuh"
+#include "umma.cuh"
+#include <stdlib.h>
+
+namespace {
+
+using namespace pv2;
+
+constexpr int kRowsPerStage = 32;   // contraction rows per pipeline stage = one 128-byte K-major line (4 MMA k-steps)
+constexpr int kABytes = 128 * 128;  // 128 output channels x 128 B
+constexpr int kMaxStages = 4;
+constexpr int kThreads = 160;
+
+struct WGParams {
+  const float* x;      // [n_in] rows of cin floats, row stride x_row, optional additive second half at +x_lo
+  int64_t x_row, x_lo;
+  const float* dyt;    // transposed split dy: [2][cout][np]  (hi plane, lo plane)
+  int64_t np;          // padded row count (multiple of 32) = row length of dyt
+  const int32_t* nbr;  // [kvol][n_out] or nullptr (identity, kvol = 1)
+  float* dw;           // [cout][kvol][cin]
+  int64_t n_out;
+  int cin, cout, kvol;
+  int n_pad;           // cin rounded up to 16
+  int64_t rows_per_chunk;
+  int stages;
+  uint32_t tmem_cols;
+};
+
+__device__ __forceinline__ void split_tf32_dev(float v, float& hi, float& lo) {
+  uint32_t h, l;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
+  hi = __uint_as_float(h);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(v - hi));
+  lo = __uint_as_float(l);
+}
+
+__global__ void __launch_bounds__(kThreads) umma_wgrad_kernel(const WGParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int k = blockIdx.y;
+  const int co0 = blockIdx.z * 128;
+  const int64_t r_begin = (int64_t)blockIdx.x * p.rows_per_chunk;
+  int64_t r_end = r_begin + p.rows_per_chunk;
+  if (r_end > p.n_out) r_end = p.n_out;
+  const int n_iters = (int)((r_end - r_begin + kRowsPerStage - 1) / kRowsPerStage);
+
+  const int b_bytes = p.n_pad * 128;
+  const int stage_bytes = 2 * (kABytes + b_bytes);   // [A_hi][A_lo][B_hi][B_lo]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kMaxStages;
+  uint64_t* tmem_full_bar = bars + 2 * kMaxStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 1);
+
+  if (tid == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(smem_u32(&full_bar[s]), 128); mbar_init(smem_u32(&empty_bar[s]), 1); }
+    mbar_init(smem_u32(tmem_full_bar), 1);
+    fence_mbar_init();
+  }
+  if (warp == 4) tmem_alloc(smem_u32(tmem_slot), p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ------------------------------- producers -------------------------------
+    const int piece = tid & 7;   // A: 16-byte piece (4 rows j) of a channel's 128-byte line
+    const int cbase = tid >> 3;  // A: channels cbase, cbase+16, ...
+    const uint32_t a_off = sw128_offset(cbase, piece);
+    const int lag = p.stages - 1;
+    const int n_units = p.n_pad / 4;
+    constexpr int kMaxUnitsPerWarp = 16;  // n_pad <= 256 -> 64 units / 4 warps
+    const int upw = n_units / 4;          // n_pad is a multiple of 16 -> n_units is a multiple of 4
+    const uint32_t col = (uint32_t)((lane & 3) * 4);
+    const int jc = lane >> 2;
+    auto load_src = [&](int it) -> int32_t {
+      const int64_t j = r_begin + (int64_t)it * kRowsPerStage + lane;
+      return (it < n_iters && j < r_end) ? (p.nbr != nullptr ? __ldg(&p.nbr[(int64_t)k * p.n_out + j]) : (int32_t)j) : -1;
+    };
+    int32_t src_next = load_src(0);
+    for (int it = 0; it < n_iters + lag; ++it) {
+      if (it < n_iters) {
+        const int s = it % p.stages;
+        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+        // B operand: every global load of this stage is issued before anything waits (latency overlaps the barrier wait
+        // and the A copies); the neighbour index of the next stage is prefetched as well
+        const int32_t src = src_next;
+        const float* xr = p.x + (int64_t)(src >= 0 ? src : 0) * p.x_row;
+        float4 xv[kMaxUnitsPerWarp];
+#pragma unroll
+        for (int q = 0; q < kMaxUnitsPerWarp; ++q) {
+          const int u = warp * upw + q;   // each lane reads one contiguous run of its row (whole sectors, fetched once)
+          xv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (q < upw && src >= 0 && u * 4 < p.cin) {
+            xv[q] = __ldg(reinterpret_cast<const float4*>(xr) + u);
+            if (p.x_lo) {
+              const float4 w = __ldg(reinterpret_cast<const float4*>(xr + p.x_lo) + u);
+              xv[q].x += w.x; xv[q].y += w.y; xv[q].z += w.z; xv[q].w += w.w;
+            }
+          }
+        }
+        src_next = load_src(it + 1);
+        mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+        uint8_t* a_hi = smem + (size_t)s * stage_bytes;
+        uint8_t* b_hi = a_hi + 2 * kABytes;
+        const int64_t j0 = r_begin + (int64_t)it * kRowsPerStage;
+        // A: rows = output channels, 128 B = dy^T[co][j0 .. j0+31]
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int c = cbase + 16 * i;
+          const bool ok = (co0 + c) < p.cout;
+          const float* g = ok ? p.dyt + ((int64_t)(co0 + c) * p.np + j0 + piece * 4) : p.dyt;
+          const uint32_t dst = smem_u32(a_hi) + a_off + i * 2048;
+          cp_async_16(dst, g, ok ? 16u : 0u);
+          cp_async_16(dst + kABytes, ok ? g + (int64_t)p.cout * p.np : p.dyt, ok ? 16u : 0u);
+        }
+        // B: lane = row j; transposing stores (bank = f(lane) only -> conflict-free)
+#pragma unroll
+        for (int q = 0; q < kMaxUnitsPerWarp; ++q) {
+          const int u = warp * upw + q;   // each lane reads one contiguous run of its row (whole sectors, fetched once)
+          if (q < upw) {
+            const float vv[4] = {xv[q].x, xv[q].y, xv[q].z, xv[q].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float h, l;
+              split_tf32_dev(vv[e], h, l);
+              const uint32_t off = sw128_offset(u * 4 + e, jc) + col;
+              *reinterpret_cast<float*>(b_hi + off) = h;
+              *reinterpret_cast<float*>(b_hi + b_bytes + off) = l;
+            }
+          }
+        }
+      }
+      cp_async_commit();
+      if (it >= lag) {
+        switch (lag) {
+          case 1: cp_async_wait<1>(); break;
+          case 2: cp_async_wait<2>(); break;
+          default: cp_async_wait<3>(); break;
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(smem_u32(&full_bar[(it - lag) % p.stages]));
+      }
+    }
+    // ------------------------------- epilogue -------------------------------
+    if (n_iters > 0) {
+      mbar_wait(smem_u32(tmem_full_bar), 0);
+      tc_fence_after();
+      const int co = co0 + warp * 32 + lane;
+      for (int col0 = 0; col0 < p.n_pad; col0 += 16) {
+        uint32_t v[16];
+        tmem_ld_x16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)col0, v);
+        tmem_ld_wait();
+        if (co >= p.cout) continue;
+        float* dst = p.dw + ((int64_t)co * p.kvol + k) * p.cin + col0;
+        if (col0 + 16 <= p.cin) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * q), "f"(__uint_as_float(v[4 * q])),
+                         "f"(__uint_as_float(v[4 * q + 1])), "f"(__uint_as_float(v[4 * q + 2])),
+                         "f"(__uint_as_float(v[4 * q + 3])) : "memory");
+        } else {
+          for (int i = 0; i < 16 && col0 + i < p.cin; ++i) atomicAdd(dst + i, __uint_as_float(v[i]));
+        }
+      }
+    }
+    tc_fence_before();
+  } else {
+    // ------------------------------- MMA issuer -------------------------------
+    const uint32_t idesc = make_idesc(2 /*TF32*/, 128, p.n_pad);
+    for (int it = 0; it < n_iters; ++it) {
+      const int s = it % p.stages;
+      const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+      mbar_wait(smem_u32(&full_bar[s]), ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint64_t dah = smem_desc_kmajor_sw128(smem_u32(smem + (size_t)s * stage_bytes));
+        const uint64_t dal = dah + (uint64_t)(kABytes >> 4);
+        const uint64_t dbh = dal + (uint64_t)(kABytes >> 4);
+        const uint64_t dbl = dbh + (uint64_t)(b_bytes >> 4);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          umma_tf32(tmem_base, dal + 2 * ks, dbh + 2 * ks, idesc, (it | ks) != 0 ? 1u : 0u);
+          umma_tf32(tmem_base, dah + 2 * ks, dbl + 2 * ks, idesc, 1u);
+          umma_tf32(tmem_base, dah + 2 * ks, dbh + 2 * ks, idesc, 1u);
+        }
+        umma_commit(smem_u32(&empty_bar[s]));
+        if (it == n_iters - 1) umma_commit(smem_u32(tmem_full_bar));
+      }
+      __syncwarp();
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// dy [rows][cols] (row stride in_row, optional additive half at +in_lo) -> out[2][cols][np] = TF32 hi / lo planes of dy^T,
+// zero-padded for rows in [rows, np).  32 x 32 tiles through shared memory: coalesced on both sides.
+__global__ void __launch_bounds__(256) transpose_split_kernel(const float* __restrict__ in, int64_t in_row, int64_t in_lo,
+                                                             float* __restrict__ out, int64_t rows, int cols, int64_t np) {
+  __shared__ float tile[32][33];
+  const int64_t r0 = (int64_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t r = r0 + ty + 8 * i;
+    const int c = c0 + tx;
+    float v = 0.f;
+    if (r < rows && c < cols) {
+      v = in[r * in_row + c];
+      if (in_lo) v += in[r * in_row + in_lo + c];
+    }
+    tile[ty + 8 * i][tx] = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = c0 + ty + 8 * i;
+    const int64_t r = r0 + tx;
+    if (c < cols && r < np) {
+      float h, l;
+      split_tf32_dev(tile[tx][ty + 8 * i], h, l);
+      out[(int64_t)c * np + r] = h;
+      out[((int64_t)cols + c) * np + r] = l;
+    }
+  }
+}
+
+int launch_wgrad(WGParams p, cudaStream_t stream) {
+  p.n_pad = (p.cin + 15) / 16 * 16;
+  p.tmem_cols = 32;
+  while ((int)p.tmem_cols < p.n_pad) p.tmem_cols <<= 1;
+  const int stage_bytes = 2 * (kABytes + p.n_pad * 128);
+  const int fixed = (2 * kMaxStages + 2) * 8 + 64 + 1024;
+  int stages = (200 * 1024 - fixed) / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) return PV2_EUNSUPPORTED;
+  p.stages = stages;
+  const int m_tiles = (p.cout + 127) / 128;
+  // ~4 CTAs per SM in total, chunks of at least 256 rows
+  int64_t chunks = (4LL * PV2_SM_COUNT + (int64_t)p.kvol * m_tiles - 1) / ((int64_t)p.kvol * m_tiles);
+  const int64_t max_chunks = (p.n_out + 255) / 256;
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  p.rows_per_chunk = ((p.n_out + chunks - 1) / chunks + kRowsPerStage - 1) / kRowsPerStage * kRowsPerStage;
+  chunks = (p.n_out + p.rows_per_chunk - 1) / p.rows_per_chunk;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(umma_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  const size_t smem = (size_t)stages * stage_bytes + fixed;
+  dim3 grid((unsigned)chunks, (unsigned)p.kvol, (unsigned)m_tiles);
+  umma_wgrad_kernel<<<grid, kThreads, smem, stream>>>(p);
+  PV2_DONE(1);
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t pv2_wgrad_workspace_bytes(int64_t n_in, int64_t n_out, int cin, int cout) {
+  if (n_in < 0 || n_out < 0) return 0;
+  const int64_t np = (n_out + 31) / 32 * 32;
+  return ((size_t)np * cout * 8 + 255) / 256 * 256;
+}
+
+// fp32 only.  x [n_in][cin] / dy [n_out][cout] may carry a row stride and an additive second half (+lo offset), so the
+// render MLP can hand over its split-precision activations directly.  Returns PV2_EUNSUPPORTED for shapes the
+// tensor-core kernel does not take (caller falls back to the SIMT kernel).
+int pv2_wgrad_umma(const float* x, int64_t x_row, int64_t x_lo, const float* dy, int64_t dy_row, int64_t dy_lo,
+                   const int32_t* nbr, float* dw, int64_t n_in, int64_t n_out, int cin, int cout, int kvol,
+                   void* workspace, size_t workspace_bytes, void* stream_) {
+  PV2_CHECK_ARG(n_in >= 0 && n_out >= 0 && cin > 0 && cout > 0 && kvol > 0);
+  if (n_out == 0 || n_in == 0) return 0;
+  PV2_CHECK_ARG(x && dy && dw);
+  if ((cin % 4) || cin > 256 || (x_row % 4) || (x_lo % 4) || ((uintptr_t)x & 15)) return PV2_EUNSUPPORTED;
+  if (nbr == nullptr && (kvol != 1 || n_in != n_out)) return PV2_EINVAL;
+  if (workspace == nullptr || workspace_bytes < pv2_wgrad_workspace_bytes(n_in, n_out, cin, cout) ||
+      ((uintptr_t)workspace & 15))
+    return PV2_EWORKSPACE;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int64_t np = (n_out + 31) / 32 * 32;
+  float* dyt = (float*)workspace;
+  dim3 tg((unsigned)(np / 32), (unsigned)((cout + 31) / 32));
+  transpose_split_kernel<<<tg, 256, 0, stream>>>(dy, dy_row, dy_lo, dyt, n_out, cout, np);
+  pv2_note_launches(1);
+  WGParams p{};
+  p.x = x; p.x_row = x_row; p.x_lo = x_lo; p.dyt = dyt; p.np = np; p.nbr = nbr; p.dw = dw;
+  p.n_out = n_out; p.cin = cin; p.cout = cout; p.kvol = kvol;
+  return launch_wgrad(p, stream);
+}
+
+}  // extern "C"

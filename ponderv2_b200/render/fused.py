@@ -39,9 +39,12 @@ def _linear(x, x_row, x_lo, presplit, w, bias, y, y_row, y_lo, y_split, act, y2,
 def _dense_wgrad(x, x_row, x_lo, dy, dy_row, dy_lo, rows, cin, cout):
     lib = _lib.load()
     dw = torch.zeros((cout, cin), dtype=torch.float32, device=dy.device)
+    ws_bytes = lib.pv2_wgrad_workspace_bytes(rows, rows, cin, cout)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dy.device)
     with torch.cuda.device(dy.device):
         _lib.check(lib.pv2_dense_wgrad(_lib.C.c_void_p(x.data_ptr()), x_row, x_lo, _lib.C.c_void_p(dy.data_ptr()), dy_row,
-                                       dy_lo, rows, cin, cout, _lib.ptr(dw), _lib.stream_ptr()), "pv2_dense_wgrad")
+                                       dy_lo, rows, cin, cout, _lib.ptr(dw), _lib.ptr(ws), ws_bytes, _lib.stream_ptr()),
+                   "pv2_dense_wgrad")
     return dw
 
 

@@ -141,10 +141,13 @@ def _wgrad(x: torch.Tensor, dy: torch.Tensor, nbr: torch.Tensor, kvol: int) -> t
     dw = torch.zeros((cout, kvol, cin), dtype=torch.float32, device=x.device)
     b = x.element_size()
     nbytes = x.shape[0] * cin * b + dy.shape[0] * cout * b + kvol * cin * cout * 4 + 4 * kvol * dy.shape[0]
+    ws_bytes = lib.pv2_wgrad_workspace_bytes(x.shape[0], dy.shape[0], cin, cout) if x.dtype == torch.float32 else 0
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes else None
     with torch.cuda.device(x.device), _lib.timed("pv2_spconv_wgrad", nbytes, 0):
         _lib.check(lib.pv2_spconv_wgrad(_lib.ptr(x.contiguous()), _lib.ptr(dy.contiguous()), _lib.ptr(nbr),
                                         _lib.ptr(dw), x.shape[0], dy.shape[0], cin, cout, kvol,
-                                        _lib.dtype_code(x.dtype), _lib.stream_ptr()), "pv2_spconv_wgrad")
+                                        _lib.dtype_code(x.dtype), _lib.ptr(ws), ws_bytes, _lib.stream_ptr()),
+                   "pv2_spconv_wgrad")
     return dw
 
 
