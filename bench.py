@@ -290,6 +290,13 @@ def run_ours(args, wl: dict) -> None:
         step(resident)
     torch.cuda.synchronize()
     log("warm-up done")
+    if args.profile_step:
+        # for `ncu --profile-from-start off`: exactly one warmed-up step inside cudaProfilerStart/Stop, no timing
+        torch.cuda.profiler.start()
+        step(resident)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
@@ -350,6 +357,8 @@ def main() -> None:
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="run one warmed-up step inside cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
