@@ -73,6 +73,14 @@ int pv2_rulebook_down(const int32_t* coords, int64_t n, const int32_t* spatial_s
 int pv2_rulebook_down_maps(const int32_t* in2out, const int32_t* koff, int64_t n, int64_t n_out,
                            int32_t* nbr_down, int32_t* nbr_up, void* stream);
 
+/* Tile order for the sparse-conv kernels: order[pos] = row, rows sorted (stably) by their neighbour-presence mask
+ * mask[j] = OR_k (nbr[k][j] >= 0) << k, so that a 128-row tile touches few distinct offsets and the (tile, offset)
+ * pairs without any neighbour can be skipped (what spconv's implicit-GEMM mask sort does).  kvol <= 32, else
+ * PV2_EUNSUPPORTED.  Convolution results never depend on the order. */
+size_t pv2_rulebook_row_order_workspace_bytes(int64_t n);
+int pv2_rulebook_row_order(const int32_t* nbr, int64_t n, int kvol, int32_t* order,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
 /* batch ids from cumulative offsets (ponder/models/utils.py:11-26 offset2batch) fused with the
  * [n,4] int32 (batch, c0, c1, c2) assembly of spconv_unet_v1m1_base.py:247-256.
  * grid_coord: [n,3] int64, offset: [b] int64 cumulative. */
@@ -87,17 +95,18 @@ int pv2_make_indices(const int64_t* grid_coord, const int64_t* offset, int64_t n
  * entry point serves forward (spconv layout [Cout,K,Cin]: strides K*Cin, Cin) and dgrad
  * (the transposed/k-flipped copy the host shim prepares).
  * ------------------------------------------------------------------------------------------ */
+/* row_order (optional, may be NULL): [n_out] permutation from pv2_rulebook_row_order grouping the output rows into tiles. */
 int pv2_spconv_gather_gemm(const void* x, const void* w, int64_t w_stride_co, int64_t w_stride_k,
-                           const float* bias, const int32_t* nbr, void* y,
+                           const float* bias, const int32_t* nbr, const int32_t* row_order, void* y,
                            int64_t n_in, int64_t n_out, int cin, int cout, int kvol,
                            int dtype, void* workspace, size_t workspace_bytes, void* stream);
-/* Scratch for the fp32 tensor-core path (3xTF32 needs hi/lo split copies of x and w); 0 for bf16.  A call with
- * less workspace than this still succeeds on the exact-fp32 SIMT kernel. */
+/* Scratch of the gather-GEMM: 0 (operands are gathered raw and split into TF32 halves on chip); kept so callers size
+ * workspaces uniformly. */
 size_t pv2_spconv_workspace_bytes(int64_t n_in, int cin, int cout, int kvol, int dtype);
 
 /* dw[co, k, ci] (+)= sum_j dy[j, co] * x[nbr[k][j], ci];  dw is float32 [Cout, K, Cin], must be
  * zeroed by the caller (accumulated with atomics across row chunks). */
-int pv2_spconv_wgrad(const void* x, const void* dy, const int32_t* nbr, float* dw,
+int pv2_spconv_wgrad(const void* x, const void* dy, const int32_t* nbr, const int32_t* row_order, float* dw,
                      int64_t n_in, int64_t n_out, int cin, int cout, int kvol,
                      int dtype, void* workspace, size_t workspace_bytes, void* stream);
 /* scratch of the fp32 tensor-core weight-gradient kernel (split-precision copies of x and dy); without it the

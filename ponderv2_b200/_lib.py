@@ -29,10 +29,12 @@ SIGNATURES = {
     "pv2_rulebook_down": (_int, [_vp, _i64, C.POINTER(C.c_int32), _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pv2_rulebook_down_maps": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp]),
     "pv2_make_indices": (_int, [_vp, _vp, _i64, _int, _vp, _vp]),
-    "pv2_spconv_gather_gemm": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _i64, _int, _int, _int, _int, _vp,
+    "pv2_rulebook_row_order_workspace_bytes": (_sz, [_i64]),
+    "pv2_rulebook_row_order": (_int, [_vp, _i64, _int, _vp, _vp, _sz, _vp]),
+    "pv2_spconv_gather_gemm": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _i64, _int, _int, _int, _int, _vp,
                                        _sz, _vp]),
     "pv2_spconv_workspace_bytes": (_sz, [_i64, _int, _int, _int, _int]),
-    "pv2_spconv_wgrad": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _int, _int, _int, _int, _vp, _sz, _vp]),
+    "pv2_spconv_wgrad": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _int, _int, _int, _int, _vp, _sz, _vp]),
     "pv2_wgrad_workspace_bytes": (_sz, [_i64, _i64, _int, _int]),
     "pv2_linear_workspace_bytes": (_sz, [_i64, _int, _int, _int]),
     "pv2_linear": (_int, [_vp, _i64, _i64, _int, _vp, _vp, _vp, _i64, _i64, _int, _int, _vp, _i64, _i64, _i64, _int, _int,

@@ -12,8 +12,8 @@ static unsigned long long g_launches = 0;
 void pv2_note_launches(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
 int64_t pv2_launch_count(void) { return (int64_t)__atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
-int pv2_spconv_gather_gemm_umma(const void*, const void*, int64_t, int64_t, const float*, const int32_t*, void*, int64_t,
-                                int64_t, int, int, int, int, void*, size_t, void*);
+int pv2_spconv_gather_gemm_umma(const void*, const void*, int64_t, int64_t, const float*, const int32_t*, const int32_t*,
+                                void*, int64_t, int64_t, int, int, int, int, void*);
 
 static int force_simt() {
   static int v = -1;
@@ -40,28 +40,30 @@ int pv2_sm_count(void) {
 }
 
 int pv2_spconv_gather_gemm(const void* x, const void* w, int64_t w_sco, int64_t w_sk, const float* bias,
-                           const int32_t* nbr, void* y, int64_t n_in, int64_t n_out, int cin, int cout, int kvol,
-                           int dtype, void* workspace, size_t workspace_bytes, void* stream) {
+                           const int32_t* nbr, const int32_t* row_order, void* y, int64_t n_in, int64_t n_out, int cin,
+                           int cout, int kvol, int dtype, void* workspace, size_t workspace_bytes, void* stream) {
+  (void)workspace; (void)workspace_bytes;
   // tensor-core implicit GEMM whenever the shape allows it (16-byte aligned channel runs, Cout <= 256, K <= 32);
   // the ragged stem (Cin = 6 / 4, K = 125) runs on the exact-fp32 SIMT kernel.  PV2_FORCE_SIMT=1 is for A/B tests.
   if (!force_simt() && (int64_t)cin * kvol >= 64) {
-    int rc = pv2_spconv_gather_gemm_umma(x, w, w_sco, w_sk, bias, nbr, y, n_in, n_out, cin, cout, kvol, dtype, workspace,
-                                         workspace_bytes, stream);
-    if (rc != PV2_EUNSUPPORTED && rc != PV2_EWORKSPACE) return rc;
+    int rc = pv2_spconv_gather_gemm_umma(x, w, w_sco, w_sk, bias, nbr, row_order, y, n_in, n_out, cin, cout, kvol, dtype,
+                                         stream);
+    if (rc != PV2_EUNSUPPORTED) return rc;
   }
   return pv2_spconv_gather_gemm_simt(x, w, w_sco, w_sk, bias, nbr, y, n_in, n_out, cin, cout, kvol, dtype, stream);
 }
 
-int pv2_wgrad_umma(const float*, int64_t, int64_t, const float*, int64_t, int64_t, const int32_t*, float*, int64_t, int64_t,
-                   int, int, int, void*, size_t, void*);
+int pv2_wgrad_umma(const float*, int64_t, int64_t, const float*, int64_t, int64_t, const int32_t*, const int32_t*, float*,
+                   int64_t, int64_t, int, int, int, void*, size_t, void*);
 
-int pv2_spconv_wgrad(const void* x, const void* dy, const int32_t* nbr, float* dw, int64_t n_in, int64_t n_out, int cin,
-                     int cout, int kvol, int dtype, void* workspace, size_t workspace_bytes, void* stream) {
+int pv2_spconv_wgrad(const void* x, const void* dy, const int32_t* nbr, const int32_t* row_order, float* dw, int64_t n_in,
+                     int64_t n_out, int cin, int cout, int kvol, int dtype, void* workspace, size_t workspace_bytes,
+                     void* stream) {
   // tensor-core wgrad pays off once the gathered rows are wide (measured on B200, 100 k voxels, K = 27:
   // 96->96 1.6 vs 2.4 ms, 256->256 6.4 vs 10.1 ms, but 32->32 1.1 vs 0.6 ms): narrow layers stay on the SIMT kernel
   if (!force_simt() && dtype == PV2_F32 && kvol <= 32 && cin >= 96) {
-    int rc = pv2_wgrad_umma((const float*)x, cin, 0, (const float*)dy, cout, 0, nbr, dw, n_in, n_out, cin, cout, kvol,
-                            workspace, workspace_bytes, stream);
+    int rc = pv2_wgrad_umma((const float*)x, cin, 0, (const float*)dy, cout, 0, nbr, row_order, dw, n_in, n_out, cin, cout,
+                            kvol, workspace, workspace_bytes, stream);
     if (rc != PV2_EUNSUPPORTED && rc != PV2_EWORKSPACE) return rc;
   }
   return pv2_spconv_wgrad_simt(x, dy, nbr, dw, n_in, n_out, cin, cout, kvol, dtype, stream);

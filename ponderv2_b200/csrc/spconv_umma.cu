@@ -3,19 +3,23 @@
 //   Y[j, :] = bias + sum_k W_k . X[nbr[k][j], :]        (SubMConv3d / SparseConv3d / SparseInverseConv3d fwd + dgrad;
 //                                                         reference call sites spconv_unet_v1m1_base.py:47-66,135-177)
 //
-// One CTA owns a tile of 128 output rows and all Cout (<= 256) columns.  The contraction runs over the concatenated
-// axis (kernel offset k, input channel ci) in chunks of 128 bytes per row:
-//   * warps 0-3 (128 threads) gather the A chunk — for output row r the 128 B come from X[nbr[k][row0+r]] (zero-filled
-//     when the neighbour is missing) — and the matching W chunk straight into the 128B-swizzled K-major layout
-//     tcgen05.mma consumes; bf16 uses cp.async (LDGSTS) with zfill, fp32 splits every value into two TF32 halves
-//     (3xTF32: hi*hi + lo*hi + hi*lo, ~2^-21 relative error, i.e. fp32-grade results from the tensor pipe);
-//   * warp 4 issues tcgen05.mma (M = 128, N = Cout padded to 16) into a TMEM accumulator, releasing smem stages with
+// One CTA owns a tile of 128 output rows and all Cout (<= 256) columns.  Which rows form a tile is given by an optional
+// `order` permutation (rows with equal neighbour masks adjacent, pv2_rulebook_row_order): a (tile, offset) pair in which
+// no row has a neighbour is skipped by every role, so mask-sorted tiles run ~K_present instead of K offsets.
+// The contraction runs over the concatenated axis (kernel offset k, input channel ci) in chunks of 128 bytes per row:
+//   * warps 0-7 are producers.  bf16: all 256 threads issue 16-byte cp.async (LDGSTS, zero-fill for missing neighbours)
+//     straight into the 128B-swizzled K-major layout tcgen05.mma consumes.  fp32: the rows are gathered RAW (4 B per
+//     element through L2, not a pre-split 8 B copy), split in registers into two TF32 halves and stored with 128-bit
+//     st.shared; two groups of four warps alternate chunks so that one group's loads are in flight while the other
+//     group splits/stores.  3xTF32 (hi*hi + lo*hi + hi*lo, ~2^-21 relative error) gives fp32-grade results from the
+//     tensor pipe;
+//   * warp 8 issues tcgen05.mma (M = 128, N = Cout padded to 16) into a TMEM accumulator, releasing smem stages with
 //     tcgen05.commit -> mbarrier;
-//   * warps 0-3 then drain TMEM (tcgen05.ld 32x32b), add the bias and write every output row exactly once (no atomics).
-// (tile, offset) pairs with no neighbour at all are skipped by both sides.
+//   * warps 0-7 then drain TMEM (tcgen05.ld 32x32b), add the bias and write every output row exactly once (no atomics).
 //
-// HBM-side algorithmic bytes per call: N*Cin*b + N*Cout*b + K*Cin*Cout*b + 4*K*N; the gather itself is served by the
-// 126 MB L2 (a feature matrix of 100 k x 96 bf16 is 19 MB).
+// The kernel is bound by L2 -> SM traffic (B200: ~6.3 KB/clk chip-wide, ~42 B/clk/SM), hence raw operands, the skipped
+// (tile, offset) pairs and the per-CTA chunk rotation that spreads co-resident CTAs over different weight lines.
+// HBM-side algorithmic bytes per call: N*Cin*b + N*Cout*b + K*Cin*Cout*b + 4*K*N.
 #include "pv2_common.cuh"
 #include "umma.cuh"
 
@@ -24,8 +28,9 @@ namespace {
 using namespace pv2;
 
 constexpr int kTileM = 128;
-constexpr int kProducerThreads = 128;
-constexpr int kThreads = 160;
+constexpr int kProducerWarps = 8;
+constexpr int kProducerThreads = kProducerWarps * 32;
+constexpr int kThreads = kProducerThreads + 32;
 constexpr int kABytes = kTileM * 128;  // one operand tile: 128 rows x 128 B
 constexpr int kMaxStages = 6;
 
@@ -35,6 +40,7 @@ struct GGParams {
   int64_t w_sco, w_sk;
   const float* bias;
   const int32_t* nbr;
+  const int32_t* order;  // optional [n_out]: tile position -> output row
   void* y;
   int64_t n_out;
   int cin, cout, kvol;
@@ -42,9 +48,8 @@ struct GGParams {
   int num_chunks;  // ceil(kvol * cin / elems_per_row)
   int stages;
   uint32_t tmem_cols;
-  int64_t x_row;     // elements between consecutive rows of x (2*cin for the split-precision format)
-  int64_t w_lo_off;  // element offset from the hi plane of w to its lo plane (split-precision format)
-  int64_t x_lo_off;  // element offset from the hi half of an x row to its lo half (split-precision format)
+  int64_t x_row;     // elements between consecutive rows of x
+  int64_t x_lo_off;  // fp32: != 0 -> x is split-precision, value = x[..] + x[.. + x_lo_off]
   // output: row stride, optional split-precision output (hi at y, lo at y + y_lo_off) and the fused epilogue
   int64_t y_row, y_lo_off;
   int y_split;       // fp32 only: write TF32 hi/lo halves instead of the plain value
@@ -53,11 +58,7 @@ struct GGParams {
   int64_t y2_row, y2_lo_off;
   int ksplit;        // > 1: gridDim.y CTAs share one row tile, each reduces a slice of the contraction and adds its
                      // partial result into the (pre-zeroed) output with red.global.add (small deep U-Net levels)
-  long long* trace;  // development only: per-chunk clock64 stamps of CTA 0 (nullptr in production)
 };
-
-long long* g_trace_ptr = nullptr;
-#define PV2_TRACE(slot, it) do { if (p.trace != nullptr && blockIdx.x == 0 && (it) < 256) p.trace[(it) * 8 + (slot)] = clock64(); } while (0)
 
 template <bool kSplit>
 struct ModeTraits;
@@ -81,25 +82,16 @@ __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
   lo = __uint_as_float(l);
 }
 
-// Split-precision storage for the 3xTF32 path.  rows x cols fp32 -> out[row][0][cols] = hi, out[row][1][cols] = lo when
-// `interleave` (activations: one gather fetches both halves), else two planes out[0][...] = hi, out[1][...] = lo (weights).
-__global__ void split_tf32_kernel(const float4* __restrict__ in, float4* __restrict__ out, int64_t rows, int cols4,
-                                  int interleave) {
-  const int64_t total = rows * cols4;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const float4 v = __ldg(&in[i]);
-    float4 h, l;
-    split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
-    if (interleave) {
-      const int64_t r = i / cols4;
-      const int c = (int)(i - r * cols4);
-      out[(r * 2) * cols4 + c] = h;
-      out[(r * 2 + 1) * cols4 + c] = l;
-    } else {
-      out[i] = h;
-      out[total + i] = l;
-    }
-  }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, const float4& v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// split a float4 and store the halves at `addr` (hi tile) and `addr + lo_delta` (lo tile)
+__device__ __forceinline__ void split_store(uint32_t addr, uint32_t lo_delta, const float4& v) {
+  float4 h, l;
+  split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+  st_shared_v4(addr, h);
+  st_shared_v4(addr + lo_delta, l);
 }
 
 template <bool kSplit>
@@ -118,7 +110,8 @@ __global__ void __launch_bounds__(kThreads) umma_gather_gemm_kernel(const GGPara
   const int stage_bytes = (kABytes + b_bytes) * T::kOperands;
   uint8_t* stage_base = smem;
   int32_t* idx_s = reinterpret_cast<int32_t*>(smem + (size_t)p.stages * stage_bytes);
-  uint16_t* active = reinterpret_cast<uint16_t*>(idx_s + p.kvol * kTileM);
+  int32_t* row_s = idx_s + p.kvol * kTileM;
+  uint16_t* active = reinterpret_cast<uint16_t*>(row_s + kTileM);
   uint64_t* bars = reinterpret_cast<uint64_t*>(
       (reinterpret_cast<uintptr_t>(active + p.num_chunks) + 7) & ~uintptr_t(7));
   uint64_t* full_bar = bars;
@@ -126,135 +119,205 @@ __global__ void __launch_bounds__(kThreads) umma_gather_gemm_kernel(const GGPara
   uint64_t* tmem_full_bar = bars + 2 * kMaxStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 1);
   uint32_t* kmask_s = tmem_slot + 1;
-  int* n_active_s = reinterpret_cast<int*>(tmem_slot + 2);
+  int* wcount_s = reinterpret_cast<int*>(tmem_slot + 2);  // [kProducerWarps + 1]
 
   // ---- setup ---------------------------------------------------------------------------------------------
-  for (int i = tid; i < p.kvol * kTileM; i += kThreads) {
-    int k = i / kTileM, r = i - k * kTileM;
-    int64_t j = row0 + r;
-    idx_s[i] = (j < p.n_out) ? (p.nbr != nullptr ? __ldg(&p.nbr[(int64_t)k * p.n_out + j]) : (int32_t)j) : -1;
+  if (tid < kTileM) {
+    const int64_t pos = row0 + tid;
+    int32_t j = -1;
+    if (pos < p.n_out) j = (p.order != nullptr) ? __ldg(&p.order[pos]) : (int32_t)pos;
+    row_s[tid] = j;
   }
   if (tid == 0) {
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(smem_u32(&full_bar[s]), kProducerThreads);
+      mbar_init(smem_u32(&full_bar[s]), kSplit ? kProducerThreads / 2 : kProducerThreads);
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
     mbar_init(smem_u32(tmem_full_bar), 1);
     *kmask_s = 0;
     fence_mbar_init();
   }
-  if (warp == 4) tmem_alloc(smem_u32(tmem_slot), p.tmem_cols);
+  if (warp == kProducerWarps) tmem_alloc(smem_u32(tmem_slot), p.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  for (int i = tid; i < p.kvol * kTileM; i += kThreads) {
+    const int k = i >> 7, r = i & (kTileM - 1);
+    const int32_t j = row_s[r];
+    idx_s[i] = (j >= 0) ? (p.nbr != nullptr ? __ldg(&p.nbr[(int64_t)k * p.n_out + j]) : j) : -1;
+  }
+  __syncthreads();
   // which kernel offsets have at least one neighbour in this tile
-  if (warp < 4) {
-    uint32_t m = 0;
-    for (int k = 0; k < p.kvol; ++k) {
-      unsigned b = __ballot_sync(0xffffffffu, idx_s[k * kTileM + tid] >= 0);
-      if (b) m |= 1u << k;
+  if (warp < kProducerWarps) {
+    for (int k = warp; k < p.kvol; k += kProducerWarps) {
+      const int32_t* r = idx_s + k * kTileM + lane;
+      const bool a = (r[0] >= 0) | (r[32] >= 0) | (r[64] >= 0) | (r[96] >= 0);
+      if (__any_sync(0xffffffffu, a) && lane == 0) atomicOr(kmask_s, 1u << k);
     }
-    if (lane == 0 && m) atomicOr(kmask_s, m);
   }
   __syncthreads();
-  if (tid == 0) {
+  // compact the chunks that touch at least one active offset (all threads take part in the barriers)
+  int n_total = 0;
+  {
     const uint32_t km = *kmask_s;
-    int n = 0;
-    for (int c = 0; c < p.num_chunks; ++c) {
-      int k_lo = (c * T::kEPR) / p.cin;
-      int k_hi = ((c + 1) * T::kEPR - 1) / p.cin;
-      if (k_hi >= p.kvol) k_hi = p.kvol - 1;
+    for (int c0 = 0; c0 < p.num_chunks; c0 += kProducerThreads) {
+      const int c = c0 + tid;
       bool on = false;
-      for (int k = k_lo; k <= k_hi; ++k) on |= ((km >> k) & 1u) != 0;
-      if (on) active[n++] = (uint16_t)c;
+      if (tid < kProducerThreads && c < p.num_chunks) {
+        const int k_lo = (c * T::kEPR) / p.cin;
+        int k_hi = ((c + 1) * T::kEPR - 1) / p.cin;
+        if (k_hi >= p.kvol) k_hi = p.kvol - 1;
+        for (int k = k_lo; k <= k_hi; ++k) on |= ((km >> k) & 1u) != 0;
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, on);
+      if (lane == 0 && warp < kProducerWarps) wcount_s[warp] = __popc(bal);
+      __syncthreads();
+      int before = 0, all = 0;
+#pragma unroll
+      for (int w2 = 0; w2 < kProducerWarps; ++w2) {
+        const int cnt = wcount_s[w2];
+        before += (w2 < warp) ? cnt : 0;
+        all += cnt;
+      }
+      if (on) active[n_total + before + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)c;
+      n_total += all;
+      __syncthreads();
     }
-    // Every CTA streams the same weight chunks; starting each tile at a different chunk spreads the L2 slices the
-    // co-resident CTAs hit at any instant (the order of accumulation is irrelevant to the sum).
-    if (n > 1) {
-      const int rot = (int)((blockIdx.x * 11u) % (unsigned)n);
-      for (int a = 0, b = rot - 1; a < b; ++a, --b) { uint16_t t = active[a]; active[a] = active[b]; active[b] = t; }
-      for (int a = rot, b = n - 1; a < b; ++a, --b) { uint16_t t = active[a]; active[a] = active[b]; active[b] = t; }
-      for (int a = 0, b = n - 1; a < b; ++a, --b) { uint16_t t = active[a]; active[a] = active[b]; active[b] = t; }
-    }
-    if (p.ksplit > 1) {  // keep only this CTA's contiguous slice of the active chunks
-      const int per = (n + p.ksplit - 1) / p.ksplit;
-      const int lo = (int)blockIdx.y * per;
-      int hi = lo + per;
-      if (hi > n) hi = n;
-      int m = 0;
-      for (int a = lo; a < hi; ++a) active[m++] = active[a];
-      n = m;
-    }
-    *n_active_s = n;
   }
-  __syncthreads();
-  const int n_active = *n_active_s;
+  // Every CTA streams the same weight chunks; starting each tile at a different chunk spreads the L2 slices the
+  // co-resident CTAs hit at any instant (the order of accumulation is irrelevant to the sum).  With split-K
+  // (gridDim.y > 1) each CTA takes a contiguous slice of the rotated list.
+  int first = 0, n_active = n_total;
+  if (p.ksplit > 1) {
+    const int per = (n_total + p.ksplit - 1) / p.ksplit;
+    first = (int)blockIdx.y * per;
+    n_active = n_total - first;
+    if (n_active > per) n_active = per;
+    if (n_active < 0) n_active = 0;
+  }
+  const int rot = (n_total > 1) ? (int)((blockIdx.x * 11u) % (unsigned)n_total) : 0;
+  auto chunk_at = [&](int it) -> int {
+    int q = first + it + rot;
+    if (q >= n_total) q -= n_total;
+    return (int)active[q];
+  };
   const int ktot = p.kvol * p.cin;
 
-  if (warp < 4) {
+  if (warp < kProducerWarps) {
     // ======================= producers =======================
-    const int piece = tid & 7;
-    const int rbase = tid >> 3;  // 0..15
     using E = typename T::Elt;
     const E* x = reinterpret_cast<const E*>(p.x);
     const E* w = reinterpret_cast<const E*>(p.w);
-    const int lag = p.stages - 1;
-    const uint32_t tile_off = sw128_offset(rbase, piece);
-    for (int it = 0; it < n_active + lag; ++it) {
-      if (it < n_active) {
-        const int c = active[it];
+    if constexpr (kSplit) {
+      const int grp = warp >> 2;       // chunks it = grp, grp + 2, ...
+      const int tg = tid & 127;
+      const int piece = tg & 7;
+      const int rbase = tg >> 3;       // 0..15; rows rbase + 16 i keep r & 7, so the swizzled offset advances 2048 B per i
+      const uint32_t tile_off = sw128_offset(rbase, piece);
+      const int nb = p.n_pad >> 4;     // weight rows per thread (1..16)
+      const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int it = grp; it < n_active; it += 2) {
+        const int c = chunk_at(it);
         const int s = it % p.stages;
         const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-        if (tid == 0) PV2_TRACE(0, it);
-        mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
-        if (tid == 0) PV2_TRACE(1, it);
-        uint8_t* a_tile = stage_base + (size_t)s * stage_bytes;
-        uint8_t* b_tile = a_tile + kABytes * T::kOperands;
         const int e0 = c * T::kEPR + piece * T::kEPP;
         const bool kvalid = e0 < ktot;
         const int k = kvalid ? e0 / p.cin : 0;
         const int ci = kvalid ? e0 - k * p.cin : 0;
         const int32_t* idx_k = idx_s + k * kTileM;
-        // all index loads first (independent LDS), then the copies back to back; row r = rbase + 16 i keeps r & 7, so
-        // the swizzled destination advances by a constant 2048 B per i
-        int32_t src[kTileM / 16];
+        // every global load of the chunk is issued before anything waits
+        float4 va[8];
 #pragma unroll
-        for (int i = 0; i < kTileM / 16; ++i) src[i] = kvalid ? idx_k[rbase + 16 * i] : -1;
-        const uint32_t a_dst = smem_u32(a_tile) + tile_off;
+        for (int i = 0; i < 8; ++i) {
+          const int32_t src = kvalid ? idx_k[rbase + 16 * i] : -1;
+          va[i] = zero4;
+          if (src >= 0) {
+            const float* g = x + ((int64_t)src * p.x_row + ci);
+            va[i] = __ldg(reinterpret_cast<const float4*>(g));
+            if (p.x_lo_off != 0) {
+              const float4 l = __ldg(reinterpret_cast<const float4*>(g + p.x_lo_off));
+              va[i].x += l.x; va[i].y += l.y; va[i].z += l.z; va[i].w += l.w;
+            }
+          }
+        }
+        const float* wk = w + ((int64_t)k * p.w_sk + ci);
+        float4 vb[8];
 #pragma unroll
-        for (int i = 0; i < kTileM / 16; ++i) {
-          const E* g = (src[i] >= 0) ? x + ((int64_t)src[i] * p.x_row + ci) : x;
-          const uint32_t nb = src[i] >= 0 ? 16u : 0u;
-          cp_async_16(a_dst + i * 2048, g, nb);
-          if constexpr (kSplit) cp_async_16(a_dst + i * 2048 + kABytes, g + p.x_lo_off, nb);  // lo half of the row
+        for (int i = 0; i < 8; ++i) {
+          const int n = rbase + 16 * i;
+          vb[i] = zero4;
+          if (kvalid && i < nb && n < p.cout) vb[i] = __ldg(reinterpret_cast<const float4*>(wk + (int64_t)n * p.w_sco));
         }
-        const uint32_t b_dst = smem_u32(b_tile) + tile_off;
-        const E* wk = w + ((int64_t)k * p.w_sk + ci);
-        for (int n = rbase, i = 0; n < p.n_pad; n += 16, ++i) {
-          const bool ok = kvalid && n < p.cout;
-          const E* g = ok ? wk + (int64_t)n * p.w_sco : w;
-          const uint32_t nb = ok ? 16u : 0u;
-          cp_async_16(b_dst + i * 2048, g, nb);
-          if constexpr (kSplit) cp_async_16(b_dst + i * 2048 + b_bytes, ok ? g + p.w_lo_off : w, nb);
+        mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+        const uint32_t a_dst = smem_u32(stage_base + (size_t)s * stage_bytes) + tile_off;
+        const uint32_t b_dst = a_dst + 2 * kABytes;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) split_store(a_dst + i * 2048, kABytes, va[i]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (i < nb) split_store(b_dst + i * 2048, (uint32_t)b_bytes, vb[i]);
+        if (nb > 8) {  // wide layers (Cout > 128): second half of the weight rows
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int n = rbase + 16 * (i + 8);
+            vb[i] = zero4;
+            if (kvalid && i + 8 < nb && n < p.cout) vb[i] = __ldg(reinterpret_cast<const float4*>(wk + (int64_t)n * p.w_sco));
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (i + 8 < nb) split_store(b_dst + (i + 8) * 2048, (uint32_t)b_bytes, vb[i]);
         }
+        fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core's async-proxy reads
+        mbar_arrive(smem_u32(&full_bar[s]));
       }
-      cp_async_commit();
-      if (tid == 0 && it < n_active) PV2_TRACE(2, it);
-      if (it >= lag) {
-        // chunk (it - lag) has landed for this thread: make it visible to the async proxy and signal
-        switch (lag) {  // wait_group needs an immediate
-          case 1: cp_async_wait<1>(); break;
-          case 2: cp_async_wait<2>(); break;
-          case 3: cp_async_wait<3>(); break;
-          case 4: cp_async_wait<4>(); break;
-          default: cp_async_wait<5>(); break;
+    } else {
+      const int piece = tid & 7;
+      const int rbase = tid >> 3;      // 0..31; rows rbase + 32 i -> +4096 B per i
+      const uint32_t tile_off = sw128_offset(rbase, piece);
+      const int lag = p.stages - 1;
+      for (int it = 0; it < n_active + lag; ++it) {
+        if (it < n_active) {
+          const int c = chunk_at(it);
+          const int s = it % p.stages;
+          const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+          mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+          uint8_t* a_tile = stage_base + (size_t)s * stage_bytes;
+          const int e0 = c * T::kEPR + piece * T::kEPP;
+          const bool kvalid = e0 < ktot;
+          const int k = kvalid ? e0 / p.cin : 0;
+          const int ci = kvalid ? e0 - k * p.cin : 0;
+          const int32_t* idx_k = idx_s + k * kTileM;
+          int32_t src[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) src[i] = kvalid ? idx_k[rbase + 32 * i] : -1;
+          const uint32_t a_dst = smem_u32(a_tile) + tile_off;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const E* g = (src[i] >= 0) ? x + ((int64_t)src[i] * p.x_row + ci) : x;
+            cp_async_16(a_dst + i * 4096, g, src[i] >= 0 ? 16u : 0u);
+          }
+          const uint32_t b_dst = a_dst + kABytes;
+          const E* wk = w + ((int64_t)k * p.w_sk + ci);
+          for (int n = rbase, i = 0; n < p.n_pad; n += 32, ++i) {
+            const bool ok = kvalid && n < p.cout;
+            cp_async_16(b_dst + i * 4096, ok ? wk + (int64_t)n * p.w_sco : w, ok ? 16u : 0u);
+          }
         }
-        if (tid == 0) PV2_TRACE(3, it - lag);
-        fence_proxy_async_smem();
-        mbar_arrive(smem_u32(&full_bar[(it - lag) % p.stages]));
-        if (tid == 0) PV2_TRACE(4, it - lag);
+        cp_async_commit();
+        if (it >= lag) {
+          // chunk (it - lag) has landed for this thread: make it visible to the async proxy and signal
+          switch (lag) {  // wait_group needs an immediate
+            case 1: cp_async_wait<1>(); break;
+            case 2: cp_async_wait<2>(); break;
+            case 3: cp_async_wait<3>(); break;
+            case 4: cp_async_wait<4>(); break;
+            default: cp_async_wait<5>(); break;
+          }
+          fence_proxy_async_smem();
+          mbar_arrive(smem_u32(&full_bar[(it - lag) % p.stages]));
+        }
       }
     }
 
@@ -263,12 +326,14 @@ __global__ void __launch_bounds__(kThreads) umma_gather_gemm_kernel(const GGPara
       mbar_wait(smem_u32(tmem_full_bar), 0);
       tc_fence_after();
     }
-    const int64_t j = row0 + warp * 32 + lane;
-    const bool row_ok = j < p.n_out;
-    for (int col0 = 0; col0 < p.n_pad; col0 += 16) {
+    const int lane_grp = warp & 3;            // TMEM lanes 32 * (warp % 4) .. + 31 are the ones this warp may read
+    const int32_t j32 = row_s[lane_grp * 32 + lane];
+    const int64_t j = j32;
+    const bool row_ok = j32 >= 0;
+    for (int col0 = (warp >> 2) * 16; col0 < p.n_pad; col0 += 32) {
       uint32_t v[16];
       if (n_active > 0) {
-        tmem_ld_x16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)col0, v);
+        tmem_ld_x16(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)col0, v);
         tmem_ld_wait();
       } else {
 #pragma unroll
@@ -353,15 +418,13 @@ __global__ void __launch_bounds__(kThreads) umma_gather_gemm_kernel(const GGPara
     }
     tc_fence_before();
   } else {
-    // ======================= MMA issuer (warp 4) =======================
+    // ======================= MMA issuer (warp 8) =======================
     const uint32_t idesc = make_idesc(T::kFmt, kTileM, p.n_pad);
     for (int it = 0; it < n_active; ++it) {
       const int s = it % p.stages;
       const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-      if (lane == 0) PV2_TRACE(5, it);
       mbar_wait(smem_u32(&full_bar[s]), ph);
       tc_fence_after();
-      if (lane == 0) PV2_TRACE(6, it);
       if (lane == 0) {
         // descriptors differ between k-steps only in the start-address field (16-byte units): +2 per 32 B
         const uint64_t da = smem_desc_kmajor_sw128(smem_u32(stage_base + (size_t)s * stage_bytes));
@@ -381,14 +444,13 @@ __global__ void __launch_bounds__(kThreads) umma_gather_gemm_kernel(const GGPara
         }
         umma_commit(smem_u32(&empty_bar[s]));               // smem stage reusable once these MMAs retire
         if (it == n_active - 1) umma_commit(smem_u32(tmem_full_bar));  // accumulator complete
-        PV2_TRACE(7, it);
       }
       __syncwarp();
     }
     tc_fence_before();
   }
   __syncthreads();
-  if (warp == 4) {
+  if (warp == kProducerWarps) {
     tc_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
   }
@@ -398,17 +460,13 @@ template <bool kSplit>
 int launch(const GGParams& p0, cudaStream_t stream) {
   using T = ModeTraits<kSplit>;
   GGParams p = p0;
-  p.trace = g_trace_ptr;
   p.n_pad = (p.cout + 15) / 16 * 16;
   p.num_chunks = (p.kvol * p.cin + T::kEPR - 1) / T::kEPR;
   p.tmem_cols = 32;
   while ((int)p.tmem_cols < p.n_pad) p.tmem_cols <<= 1;
   const int stage_bytes = (kABytes + p.n_pad * 128) * T::kOperands;
-  const int fixed = p.kvol * kTileM * 4 + p.num_chunks * 2 + 8 + (2 * kMaxStages + 1) * 8 + 64 + 1024;
-  // prefer two resident CTAs per SM (one's epilogue overlaps the other's main loop); fall back to one big CTA
-  int budget = 110 * 1024 - fixed;
-  int stages = budget / stage_bytes;
-  if (stages < 3) { budget = 220 * 1024 - fixed; stages = budget / stage_bytes; }
+  const int fixed = p.kvol * kTileM * 4 + kTileM * 4 + (p.num_chunks * 2 + 8) + (2 * kMaxStages + 1) * 8 + 128 + 1024;
+  int stages = (220 * 1024 - fixed) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return PV2_EUNSUPPORTED;
   p.stages = stages;
@@ -442,96 +500,60 @@ int launch(const GGParams& p0, cudaStream_t stream) {
 
 extern "C" {
 
-// development hook: device buffer (>= 2048 int64) receiving CTA 0's per-chunk clock stamps; NULL disables
-void pv2_debug_set_trace(long long* ptr) { g_trace_ptr = ptr; }
-
-// bytes of workspace the fp32 (3xTF32) path needs for the split-precision copies of x and w
+// The raw-operand fp32 path needs no scratch; kept in the ABI (returns 0) so callers can size a workspace uniformly.
 size_t pv2_spconv_workspace_bytes(int64_t n_in, int cin, int cout, int kvol, int dtype) {
-  if (dtype != PV2_F32 || n_in < 0) return 0;
-  size_t xs = ((size_t)n_in * cin * 2 * 4 + 255) / 256 * 256;
-  size_t ws = ((size_t)cout * kvol * cin * 2 * 4 + 255) / 256 * 256;
-  return xs + ws;
+  (void)n_in; (void)cin; (void)cout; (void)kvol; (void)dtype;
+  return 0;
 }
 
 // returns PV2_EUNSUPPORTED when the shape does not fit the tensor-core kernel (caller falls back to the SIMT kernel)
 int pv2_spconv_gather_gemm_umma(const void* x, const void* w, int64_t w_sco, int64_t w_sk, const float* bias,
-                                const int32_t* nbr, void* y, int64_t n_in, int64_t n_out, int cin, int cout, int kvol,
-                                int dtype, void* workspace, size_t workspace_bytes, void* stream_) {
+                                const int32_t* nbr, const int32_t* order, void* y, int64_t n_in, int64_t n_out, int cin,
+                                int cout, int kvol, int dtype, void* stream_) {
   PV2_CHECK_ARG(n_in >= 0 && n_out >= 0 && cin > 0 && cout > 0 && kvol > 0);
   if (n_out == 0) return 0;
   PV2_CHECK_ARG(x && w && nbr && y);
   const int epp = (dtype == PV2_BF16) ? 8 : 4;
   if (kvol > 32 || cout > 256 || (cin % epp) != 0 || (w_sco % epp) != 0 || (w_sk % epp) != 0) return PV2_EUNSUPPORTED;
   if (((uintptr_t)x & 15) || ((uintptr_t)w & 15) || ((uintptr_t)y & 15)) return PV2_EUNSUPPORTED;
+  if (dtype != PV2_BF16 && dtype != PV2_F32) return PV2_EUNSUPPORTED;
   GGParams p{};
-  p.x = x; p.w = w; p.w_sco = w_sco; p.w_sk = w_sk; p.bias = bias; p.nbr = nbr; p.y = y;
+  p.x = x; p.w = w; p.w_sco = w_sco; p.w_sk = w_sk; p.bias = bias; p.nbr = nbr; p.order = order; p.y = y;
   p.n_out = n_out; p.cin = cin; p.cout = cout; p.kvol = kvol;
-  p.x_row = cin; p.w_lo_off = 0; p.x_lo_off = 0;
+  p.x_row = cin; p.x_lo_off = 0;
   p.y_row = cout; p.y_lo_off = 0; p.y_split = 0; p.act = 0; p.y2 = nullptr; p.y2_row = 0; p.y2_lo_off = 0;
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (dtype == PV2_BF16) return launch<false>(p, stream);
-  if (dtype == PV2_F32) {
-    // the weight slab must be one contiguous [cout][kvol][cin] block to be split plane-wise
-    if (w_sk != cin || w_sco != (int64_t)kvol * cin) return PV2_EUNSUPPORTED;
-    const size_t need = pv2_spconv_workspace_bytes(n_in, cin, cout, kvol, dtype);
-    if (workspace == nullptr || workspace_bytes < need || ((uintptr_t)workspace & 15)) return PV2_EWORKSPACE;
-    float* xs = (float*)workspace;
-    float* ws = (float*)((char*)workspace + ((size_t)n_in * cin * 2 * 4 + 255) / 256 * 256);
-    const int64_t welems = (int64_t)cout * kvol * cin;
-    split_tf32_kernel<<<pv2_grid_for(n_in * (cin / 4), 256), 256, 0, stream>>>((const float4*)x, (float4*)xs, n_in, cin / 4, 1);
-    split_tf32_kernel<<<pv2_grid_for(welems / 4, 256), 256, 0, stream>>>((const float4*)w, (float4*)ws, welems / 4, 1, 0);
-    pv2_note_launches(2);
-    p.x = xs; p.x_row = 2 * (int64_t)cin; p.x_lo_off = cin;
-    p.w = ws; p.w_lo_off = welems;
-    return launch<true>(p, stream);
-  }
-  return PV2_EUNSUPPORTED;
+  return dtype == PV2_BF16 ? launch<false>(p, stream) : launch<true>(p, stream);
 }
 
 // ------------------------------------------------------------------------------------------------------------
 // Dense per-row linear layer on the same tensor-core kernel (identity row map): the render MLP (decoders.py:6-109).
 //   y[j, 0:cout] = act( x[j, 0:cin] . w[0:cout, 0:cin]^T + bias )          fp32 storage, 3xTF32 arithmetic
-// x may already be in split-precision form (hi at x[j*x_row + c], lo at x[j*x_row + x_lo_off + c]); otherwise it is
-// split into the workspace first.  y / y2 can be written plain or split (so the next layer needs no split pass).
+// x is plain fp32 (x_presplit = 0) or split-precision (hi at x[j*x_row + c], lo at +x_lo_off; the halves are summed on
+// load).  y / y2 can be written plain or split.
 size_t pv2_linear_workspace_bytes(int64_t rows, int cin, int cout, int x_presplit) {
-  size_t xs = x_presplit ? 0 : ((size_t)rows * cin * 2 * 4 + 255) / 256 * 256;
-  size_t ws = ((size_t)cout * cin * 2 * 4 + 255) / 256 * 256;
-  return xs + ws;
+  (void)rows; (void)cin; (void)cout; (void)x_presplit;
+  return 0;
 }
 
 int pv2_linear(const float* x, int64_t x_row, int64_t x_lo_off, int x_presplit, const float* w, const float* bias,
                float* y, int64_t y_row, int64_t y_lo_off, int y_split, int act, float* y2, int64_t y2_row,
                int64_t y2_lo_off, int64_t rows, int cin, int cout, void* workspace, size_t workspace_bytes,
                void* stream_) {
+  (void)workspace; (void)workspace_bytes;
   PV2_CHECK_ARG(rows >= 0 && cin > 0 && cout > 0 && cout <= 256 && (cin % 4) == 0 && act >= 0 && act <= 1);
   if (rows == 0) return 0;
-  PV2_CHECK_ARG(x && w && y && workspace);
+  PV2_CHECK_ARG(x && w && y);
   PV2_CHECK_ARG((x_row % 4) == 0 && (x_lo_off % 4) == 0 && (((uintptr_t)x | (uintptr_t)w | (uintptr_t)y) & 15) == 0);
   PV2_CHECK_ARG(!x_presplit || x_lo_off > 0);
-  if (workspace_bytes < pv2_linear_workspace_bytes(rows, cin, cout, x_presplit)) return PV2_EWORKSPACE;
-  cudaStream_t stream = (cudaStream_t)stream_;
-  char* wsp = (char*)workspace;
+  PV2_CHECK_ARG(x_presplit || x_row >= cin);
   GGParams p{};
-  int launches = 1;
-  if (!x_presplit) {
-    PV2_CHECK_ARG(x_row == cin);  // the split pass reads a dense [rows, cin] matrix
-    float* xs = (float*)wsp;
-    wsp += ((size_t)rows * cin * 2 * 4 + 255) / 256 * 256;
-    split_tf32_kernel<<<pv2_grid_for(rows * (cin / 4), 256), 256, 0, stream>>>((const float4*)x, (float4*)xs, rows, cin / 4, 1);
-    p.x = xs; p.x_row = 2 * (int64_t)cin; p.x_lo_off = cin;
-    ++launches;
-  } else {
-    p.x = x; p.x_row = x_row; p.x_lo_off = x_lo_off;
-  }
-  float* wsplit = (float*)wsp;
-  const int64_t welems = (int64_t)cout * cin;
-  split_tf32_kernel<<<pv2_grid_for(welems / 4, 256), 256, 0, stream>>>((const float4*)w, (float4*)wsplit, welems / 4, 1, 0);
-  pv2_note_launches(launches);
-  p.w = wsplit; p.w_sco = cin; p.w_sk = cin; p.w_lo_off = welems;
-  p.bias = bias; p.nbr = nullptr; p.y = y; p.n_out = rows; p.cin = cin; p.cout = cout; p.kvol = 1;
+  p.x = x; p.x_row = x_row; p.x_lo_off = x_presplit ? x_lo_off : 0;
+  p.w = w; p.w_sco = cin; p.w_sk = cin;
+  p.bias = bias; p.nbr = nullptr; p.order = nullptr; p.y = y; p.n_out = rows; p.cin = cin; p.cout = cout; p.kvol = 1;
   p.y_row = y_row; p.y_lo_off = y_lo_off; p.y_split = y_split; p.act = act;
   p.y2 = y2; p.y2_row = y2_row; p.y2_lo_off = y2_lo_off;
-  return launch<true>(p, stream);
+  return launch<true>(p, (cudaStream_t)stream_);
 }
 
 }  // extern "C"

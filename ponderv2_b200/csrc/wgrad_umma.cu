@@ -32,6 +32,8 @@ struct WGParams {
   const float* dyt;    // transposed split dy: [2][cout][np]  (hi plane, lo plane)
   int64_t np;          // padded row count (multiple of 32) = row length of dyt
   const int32_t* nbr;  // [kvol][n_out] or nullptr (identity, kvol = 1)
+  const int32_t* order;  // optional [n_out]: position -> row (mask-sorted, pv2_rulebook_row_order); dyt is in this order
+  int max_iters;       // rows_per_chunk / 32 (capacity of the active-stage list)
   float* dw;           // [cout][kvol][cin]
   int64_t n_out;
   int cin, cout, kvol;
@@ -67,6 +69,41 @@ __global__ void __launch_bounds__(kThreads) umma_wgrad_kernel(const WGParams p) 
   uint64_t* empty_bar = bars + kMaxStages;
   uint64_t* tmem_full_bar = bars + 2 * kMaxStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 1);
+  int* n_act_s = reinterpret_cast<int*>(tmem_slot + 1);
+  uint16_t* list_s = reinterpret_cast<uint16_t*>(tmem_slot + 2);   // [max_iters] active 32-row stages, ascending
+  uint8_t* flag_s = reinterpret_cast<uint8_t*>(list_s + p.max_iters);
+
+  // Which 32-row stages of this (row chunk, offset k) contain at least one pair?  With mask-sorted rows most stages of
+  // an offset are empty (a surface voxel has ~9 of 27 neighbours); they are skipped by producers and MMA issuer alike.
+  int n_act = n_iters;
+  if (p.nbr != nullptr) {
+    for (int st = warp; st < n_iters; st += kThreads / 32) {
+      const int64_t pos = r_begin + (int64_t)st * kRowsPerStage + lane;
+      int32_t src = -1;
+      if (pos < r_end) {
+        const int64_t j = (p.order != nullptr) ? (int64_t)__ldg(&p.order[pos]) : pos;
+        src = __ldg(&p.nbr[(int64_t)k * p.n_out + j]);
+      }
+      const bool any = __any_sync(0xffffffffu, src >= 0);
+      if (lane == 0) flag_s[st] = any ? 1 : 0;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      int cnt = 0;
+      for (int b0 = 0; b0 < n_iters; b0 += 32) {
+        const int st = b0 + lane;
+        const bool on = st < n_iters && flag_s[st] != 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, on);
+        if (on) list_s[cnt + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)st;
+        cnt += __popc(bal);
+      }
+      if (lane == 0) *n_act_s = cnt;
+    }
+    __syncthreads();
+    n_act = *n_act_s;
+    if (n_act == 0) return;   // uniform for the CTA; nothing allocated yet
+  }
+  auto stage_at = [&](int it) -> int { return (p.nbr != nullptr) ? (int)list_s[it] : it; };
 
   if (tid == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(smem_u32(&full_bar[s]), 128); mbar_init(smem_u32(&empty_bar[s]), 1); }
@@ -91,12 +128,16 @@ __global__ void __launch_bounds__(kThreads) umma_wgrad_kernel(const WGParams p) 
     const uint32_t col = (uint32_t)((lane & 3) * 4);
     const int jc = lane >> 2;
     auto load_src = [&](int it) -> int32_t {
-      const int64_t j = r_begin + (int64_t)it * kRowsPerStage + lane;
-      return (it < n_iters && j < r_end) ? (p.nbr != nullptr ? __ldg(&p.nbr[(int64_t)k * p.n_out + j]) : (int32_t)j) : -1;
+      if (it >= n_act) return -1;
+      const int64_t pos = r_begin + (int64_t)stage_at(it) * kRowsPerStage + lane;
+      if (pos >= r_end) return -1;
+      if (p.nbr == nullptr) return (int32_t)pos;
+      const int64_t j = (p.order != nullptr) ? (int64_t)__ldg(&p.order[pos]) : pos;
+      return __ldg(&p.nbr[(int64_t)k * p.n_out + j]);
     };
     int32_t src_next = load_src(0);
-    for (int it = 0; it < n_iters + lag; ++it) {
-      if (it < n_iters) {
+    for (int it = 0; it < n_act + lag; ++it) {
+      if (it < n_act) {
         const int s = it % p.stages;
         const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
         // B operand: every global load of this stage is issued before anything waits (latency overlaps the barrier wait
@@ -120,7 +161,7 @@ __global__ void __launch_bounds__(kThreads) umma_wgrad_kernel(const WGParams p) 
         mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
         uint8_t* a_hi = smem + (size_t)s * stage_bytes;
         uint8_t* b_hi = a_hi + 2 * kABytes;
-        const int64_t j0 = r_begin + (int64_t)it * kRowsPerStage;
+        const int64_t j0 = r_begin + (int64_t)stage_at(it) * kRowsPerStage;   // position (column of dyt), not row id
         // A: rows = output channels, 128 B = dy^T[co][j0 .. j0+31]
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -160,7 +201,7 @@ __global__ void __launch_bounds__(kThreads) umma_wgrad_kernel(const WGParams p) 
       }
     }
     // ------------------------------- epilogue -------------------------------
-    if (n_iters > 0) {
+    if (n_act > 0) {
       mbar_wait(smem_u32(tmem_full_bar), 0);
       tc_fence_after();
       const int co = co0 + warp * 32 + lane;
@@ -185,7 +226,7 @@ __global__ void __launch_bounds__(kThreads) umma_wgrad_kernel(const WGParams p) 
   } else {
     // ------------------------------- MMA issuer -------------------------------
     const uint32_t idesc = make_idesc(2 /*TF32*/, 128, p.n_pad);
-    for (int it = 0; it < n_iters; ++it) {
+    for (int it = 0; it < n_act; ++it) {
       const int s = it % p.stages;
       const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
       mbar_wait(smem_u32(&full_bar[s]), ph);
@@ -202,7 +243,7 @@ __global__ void __launch_bounds__(kThreads) umma_wgrad_kernel(const WGParams p) 
           umma_tf32(tmem_base, dah + 2 * ks, dbh + 2 * ks, idesc, 1u);
         }
         umma_commit(smem_u32(&empty_bar[s]));
-        if (it == n_iters - 1) umma_commit(smem_u32(tmem_full_bar));
+        if (it == n_act - 1) umma_commit(smem_u32(tmem_full_bar));
       }
       __syncwarp();
     }
@@ -218,7 +259,8 @@ __global__ void __launch_bounds__(kThreads) umma_wgrad_kernel(const WGParams p) 
 // dy [rows][cols] (row stride in_row, optional additive half at +in_lo) -> out[2][cols][np] = TF32 hi / lo planes of dy^T,
 // zero-padded for rows in [rows, np).  32 x 32 tiles through shared memory: coalesced on both sides.
 __global__ void __launch_bounds__(256) transpose_split_kernel(const float* __restrict__ in, int64_t in_row, int64_t in_lo,
-                                                             float* __restrict__ out, int64_t rows, int cols, int64_t np) {
+                                                             const int32_t* __restrict__ order, float* __restrict__ out,
+                                                             int64_t rows, int cols, int64_t np) {
   __shared__ float tile[32][33];
   const int64_t r0 = (int64_t)blockIdx.x * 32;
   const int c0 = blockIdx.y * 32;
@@ -229,8 +271,9 @@ __global__ void __launch_bounds__(256) transpose_split_kernel(const float* __res
     const int c = c0 + tx;
     float v = 0.f;
     if (r < rows && c < cols) {
-      v = in[r * in_row + c];
-      if (in_lo) v += in[r * in_row + in_lo + c];
+      const int64_t rr = (order != nullptr) ? (int64_t)__ldg(&order[r]) : r;   // column r of out = row order[r] of in
+      v = in[rr * in_row + c];
+      if (in_lo) v += in[rr * in_row + in_lo + c];
     }
     tile[ty + 8 * i][tx] = v;
   }
@@ -253,8 +296,8 @@ int launch_wgrad(WGParams p, cudaStream_t stream) {
   p.tmem_cols = 32;
   while ((int)p.tmem_cols < p.n_pad) p.tmem_cols <<= 1;
   const int stage_bytes = 2 * (kABytes + p.n_pad * 128);
-  const int fixed = (2 * kMaxStages + 2) * 8 + 64 + 1024;
-  int stages = (200 * 1024 - fixed) / stage_bytes;
+  int fixed = (2 * kMaxStages + 2) * 8 + 64 + 1024;   // + the active-stage list, added below
+  int stages = (194 * 1024 - fixed) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return PV2_EUNSUPPORTED;
   p.stages = stages;
@@ -264,8 +307,12 @@ int launch_wgrad(WGParams p, cudaStream_t stream) {
   const int64_t max_chunks = (p.n_out + 255) / 256;
   if (chunks > max_chunks) chunks = max_chunks;
   if (chunks < 1) chunks = 1;
+  const int64_t min_chunks = (p.n_out + 65535) / 65536;   // <= 2048 stages per CTA (uint16 list in shared memory)
+  if (chunks < min_chunks) chunks = min_chunks;
   p.rows_per_chunk = ((p.n_out + chunks - 1) / chunks + kRowsPerStage - 1) / kRowsPerStage * kRowsPerStage;
   chunks = (p.n_out + p.rows_per_chunk - 1) / p.rows_per_chunk;
+  p.max_iters = (int)(p.rows_per_chunk / kRowsPerStage);
+  fixed += 3 * p.max_iters + 16;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(umma_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -292,7 +339,7 @@ size_t pv2_wgrad_workspace_bytes(int64_t n_in, int64_t n_out, int cin, int cout)
 // render MLP can hand over its split-precision activations directly.  Returns PV2_EUNSUPPORTED for shapes the
 // tensor-core kernel does not take (caller falls back to the SIMT kernel).
 int pv2_wgrad_umma(const float* x, int64_t x_row, int64_t x_lo, const float* dy, int64_t dy_row, int64_t dy_lo,
-                   const int32_t* nbr, float* dw, int64_t n_in, int64_t n_out, int cin, int cout, int kvol,
+                   const int32_t* nbr, const int32_t* order, float* dw, int64_t n_in, int64_t n_out, int cin, int cout, int kvol,
                    void* workspace, size_t workspace_bytes, void* stream_) {
   PV2_CHECK_ARG(n_in >= 0 && n_out >= 0 && cin > 0 && cout > 0 && kvol > 0);
   if (n_out == 0 || n_in == 0) return 0;
@@ -306,10 +353,11 @@ int pv2_wgrad_umma(const float* x, int64_t x_row, int64_t x_lo, const float* dy,
   const int64_t np = (n_out + 31) / 32 * 32;
   float* dyt = (float*)workspace;
   dim3 tg((unsigned)(np / 32), (unsigned)((cout + 31) / 32));
-  transpose_split_kernel<<<tg, 256, 0, stream>>>(dy, dy_row, dy_lo, dyt, n_out, cout, np);
+  transpose_split_kernel<<<tg, 256, 0, stream>>>(dy, dy_row, dy_lo, order, dyt, n_out, cout, np);
   pv2_note_launches(1);
   WGParams p{};
-  p.x = x; p.x_row = x_row; p.x_lo = x_lo; p.dyt = dyt; p.np = np; p.nbr = nbr; p.dw = dw;
+  p.x = x; p.x_row = x_row; p.x_lo = x_lo; p.dyt = dyt; p.np = np; p.nbr = nbr; p.order = (nbr != nullptr) ? order : nullptr;
+  p.dw = dw;
   p.n_out = n_out; p.cin = cin; p.cout = cout; p.kvol = kvol;
   return launch_wgrad(p, stream);
 }

@@ -17,6 +17,7 @@ All arithmetic runs in hand-written sm_100a kernels; there is no CPU path (CPU t
 from __future__ import annotations
 
 import math
+import os
 from collections import OrderedDict
 from typing import List, Optional, Sequence, Union
 
@@ -24,6 +25,9 @@ import torch
 from torch import nn
 
 from .. import _lib
+
+# development switch (A/B timing of the mask-sorted tile order); results never depend on it
+USE_ROW_ORDER = os.environ.get("PV2_ROW_ORDER", "1") != "0"
 
 __all__ = [
     "SparseConvTensor", "SparseModule", "SparseSequential", "SubMConv3d", "SparseConv3d",
@@ -34,13 +38,31 @@ __all__ = [
 # ----------------------------------------------------------------------------------------------
 # rulebooks
 # ----------------------------------------------------------------------------------------------
-class SubMRulebook:
-    """nbr[k][j] = input row feeding output row j through kernel offset k, or -1."""
+def build_row_order(nbr: torch.Tensor) -> Optional[torch.Tensor]:
+    """order[pos] = row: rows sorted by neighbour-presence mask so that 128-row tiles touch few kernel offsets
+    (pv2_rulebook_row_order).  None for maps the tile-skipping kernels do not use (K > 32, empty)."""
+    kvol, n = nbr.shape
+    if kvol > 32 or kvol < 2 or n == 0:
+        return None
+    lib = _lib.load()
+    order = torch.empty(n, dtype=torch.int32, device=nbr.device)
+    ws_bytes = lib.pv2_rulebook_row_order_workspace_bytes(n)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=nbr.device)
+    with torch.cuda.device(nbr.device):
+        _lib.check(lib.pv2_rulebook_row_order(_lib.ptr(nbr), n, kvol, _lib.ptr(order), _lib.ptr(ws), ws_bytes,
+                                              _lib.stream_ptr()), "pv2_rulebook_row_order")
+    return order
 
-    def __init__(self, nbr: torch.Tensor, ksize: int, pair_count: Optional[torch.Tensor]):
+
+class SubMRulebook:
+    """nbr[k][j] = input row feeding output row j through kernel offset k, or -1; `order` groups rows into tiles."""
+
+    def __init__(self, nbr: torch.Tensor, ksize: int, pair_count: Optional[torch.Tensor],
+                 order: Optional[torch.Tensor] = None):
         self.nbr = nbr
         self.ksize = ksize
         self._pair_count = pair_count
+        self.order = order
 
     @property
     def num_pairs(self) -> int:
@@ -59,6 +81,8 @@ class DownRulebook:
         self.koff = koff
         self.nbr_down = nbr_down  # [8, n_out]
         self.nbr_up = nbr_up      # [8, n_in]
+        self.order_down = build_row_order(nbr_down)   # tile order of the coarse rows
+        self.order_up = build_row_order(nbr_up)       # tile order of the fine rows (one offset per row -> 8x fewer chunks)
 
 
 def _check_indices(indices: torch.Tensor) -> None:
@@ -82,7 +106,7 @@ def build_subm_rulebook(indices: torch.Tensor, spatial_shape: Sequence[int], ksi
         _lib.check(lib.pv2_rulebook_subm(_lib.ptr(indices), n, _lib.i32x3(spatial_shape), ksize, _lib.ptr(nbr),
                                          _lib.ptr(pc), _lib.ptr(ws), ws_bytes, _lib.stream_ptr()),
                    "pv2_rulebook_subm")
-    return SubMRulebook(nbr, ksize, pc)
+    return SubMRulebook(nbr, ksize, pc, build_row_order(nbr) if USE_ROW_ORDER else None)
 
 
 def build_down_rulebook(indices: torch.Tensor, spatial_shape: Sequence[int]) -> DownRulebook:
@@ -114,8 +138,9 @@ def build_down_rulebook(indices: torch.Tensor, spatial_shape: Sequence[int]) -> 
 # arithmetic
 # ----------------------------------------------------------------------------------------------
 def _gather_gemm(x: torch.Tensor, w3: torch.Tensor, bias: Optional[torch.Tensor], nbr: torch.Tensor,
-                 n_out: int) -> torch.Tensor:
-    """y[j] = bias + sum_k w3[:, k, :] @ x[nbr[k][j]];  w3 is [Cout, K, Cin] (any strides with unit Cin stride)."""
+                 n_out: int, order: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y[j] = bias + sum_k w3[:, k, :] @ x[nbr[k][j]];  w3 is [Cout, K, Cin] (any strides with unit Cin stride).
+    `order` ([n_out] int32, optional) is the tile order of the output rows (build_row_order)."""
     lib = _lib.load()
     cout, kvol, cin = w3.shape
     assert w3.stride(2) == 1
@@ -129,13 +154,15 @@ def _gather_gemm(x: torch.Tensor, w3: torch.Tensor, bias: Optional[torch.Tensor]
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes else None
     with torch.cuda.device(x.device), _lib.timed("pv2_spconv_gather_gemm", nbytes, 0):
         _lib.check(lib.pv2_spconv_gather_gemm(_lib.ptr(x), _lib.C.c_void_p(w3.data_ptr()), w3.stride(0), w3.stride(1),
-                                              _lib.ptr(bias), _lib.ptr(nbr), _lib.ptr(y), x.shape[0], n_out, cin,
+                                              _lib.ptr(bias), _lib.ptr(nbr), _lib.ptr(order), _lib.ptr(y), x.shape[0],
+                                              n_out, cin,
                                               cout, kvol, dcode, _lib.ptr(ws), ws_bytes, _lib.stream_ptr()),
                    "pv2_spconv_gather_gemm")
     return y
 
 
-def _wgrad(x: torch.Tensor, dy: torch.Tensor, nbr: torch.Tensor, kvol: int) -> torch.Tensor:
+def _wgrad(x: torch.Tensor, dy: torch.Tensor, nbr: torch.Tensor, kvol: int,
+           order: Optional[torch.Tensor] = None) -> torch.Tensor:
     lib = _lib.load()
     cin, cout = x.shape[1], dy.shape[1]
     dw = torch.zeros((cout, kvol, cin), dtype=torch.float32, device=x.device)
@@ -145,7 +172,7 @@ def _wgrad(x: torch.Tensor, dy: torch.Tensor, nbr: torch.Tensor, kvol: int) -> t
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes else None
     with torch.cuda.device(x.device), _lib.timed("pv2_spconv_wgrad", nbytes, 0):
         _lib.check(lib.pv2_spconv_wgrad(_lib.ptr(x.contiguous()), _lib.ptr(dy.contiguous()), _lib.ptr(nbr),
-                                        _lib.ptr(dw), x.shape[0], dy.shape[0], cin, cout, kvol,
+                                        _lib.ptr(order), _lib.ptr(dw), x.shape[0], dy.shape[0], cin, cout, kvol,
                                         _lib.dtype_code(x.dtype), _lib.ptr(ws), ws_bytes, _lib.stream_ptr()),
                    "pv2_spconv_wgrad")
     return dw
@@ -156,7 +183,7 @@ class _SparseConvFunction(torch.autograd.Function):
     `flip` mirrors the kernel offsets for the data gradient (submanifold symmetry: nbr[k][j]=i <=> nbr[K-1-k][i]=j)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, nbr_fwd, nbr_bwd, n_out: int, flip: bool):
+    def forward(ctx, x, weight, bias, nbr_fwd, nbr_bwd, n_out: int, flip: bool, order_fwd=None, order_bwd=None):
         cout, cin = weight.shape[0], weight.shape[-1]
         compute_dtype = x.dtype
         if torch.is_autocast_enabled():
@@ -166,8 +193,9 @@ class _SparseConvFunction(torch.autograd.Function):
         xc = x.to(compute_dtype)
         w3 = weight.reshape(cout, -1, cin).to(compute_dtype)
         b = bias.float() if bias is not None else None
-        y = _gather_gemm(xc, w3, b, nbr_fwd, n_out)
+        y = _gather_gemm(xc, w3, b, nbr_fwd, n_out, order_fwd)
         ctx.save_for_backward(xc, w3, nbr_fwd, nbr_bwd)
+        ctx.order_fwd, ctx.order_bwd = order_fwd, order_bwd
         ctx.flip = flip
         ctx.has_bias = bias is not None
         ctx.weight_shape = weight.shape
@@ -183,12 +211,12 @@ class _SparseConvFunction(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             wt = w3.flip(1) if ctx.flip else w3
             wt = wt.permute(2, 1, 0).contiguous()  # [Cin, K, Cout]
-            dx = _gather_gemm(dy, wt, None, nbr_bwd, xc.shape[0]).to(ctx.x_dtype)
+            dx = _gather_gemm(dy, wt, None, nbr_bwd, xc.shape[0], ctx.order_bwd).to(ctx.x_dtype)
         if ctx.needs_input_grad[1]:
-            dw = _wgrad(xc, dy, nbr_fwd, w3.shape[1]).reshape(ctx.weight_shape).to(ctx.weight_dtype)
+            dw = _wgrad(xc, dy, nbr_fwd, w3.shape[1], ctx.order_fwd).reshape(ctx.weight_shape).to(ctx.weight_dtype)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = dy.float().sum(0)
-        return dx, dw, db, None, None, None, None
+        return dx, dw, db, None, None, None, None, None, None
 
 
 # ----------------------------------------------------------------------------------------------
@@ -352,7 +380,7 @@ class SubMConv3d(_SparseConvBase):
                     input.indice_dict[self.indice_key] = rb
             elif not isinstance(rb, SubMRulebook) or rb.ksize != ks[0] or rb.nbr.shape[1] != n:
                 raise ValueError(f"indice_key {self.indice_key!r} holds a rulebook of a different conv")
-        y = _SparseConvFunction.apply(input.features, self.weight, self.bias, rb.nbr, rb.nbr, n, True)
+        y = _SparseConvFunction.apply(input.features, self.weight, self.bias, rb.nbr, rb.nbr, n, True, rb.order, rb.order)
         return input.replace_feature(y)
 
 
@@ -366,7 +394,8 @@ class SparseConv3d(_SparseConvBase):
             if self.indice_key is not None:
                 input.indice_dict[self.indice_key] = rb
         n_out = rb.out_indices.shape[0]
-        y = _SparseConvFunction.apply(input.features, self.weight, self.bias, rb.nbr_down, rb.nbr_up, n_out, False)
+        y = _SparseConvFunction.apply(input.features, self.weight, self.bias, rb.nbr_down, rb.nbr_up, n_out, False,
+                                      rb.order_down if USE_ROW_ORDER else None, rb.order_up if USE_ROW_ORDER else None)
         return SparseConvTensor(y, rb.out_indices, rb.out_shape, input.batch_size, input.grid, input.voxel_num,
                                 input.indice_dict, input.benchmark)
 
@@ -382,6 +411,7 @@ class SparseInverseConv3d(_SparseConvBase):
         if self.kernel_size != [2, 2, 2]:
             raise NotImplementedError("SparseInverseConv3d: kernel_size=2 only")
         n_fine = rb.in_indices.shape[0]
-        y = _SparseConvFunction.apply(input.features, self.weight, self.bias, rb.nbr_up, rb.nbr_down, n_fine, False)
+        y = _SparseConvFunction.apply(input.features, self.weight, self.bias, rb.nbr_up, rb.nbr_down, n_fine, False,
+                                      rb.order_up if USE_ROW_ORDER else None, rb.order_down if USE_ROW_ORDER else None)
         return SparseConvTensor(y, rb.in_indices, rb.in_shape, input.batch_size, input.grid, input.voxel_num,
                                 input.indice_dict, input.benchmark)

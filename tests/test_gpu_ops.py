@@ -99,6 +99,28 @@ def test_down_rulebook_canonical_bit_exact(cuda_lib, case):
     assert np.array_equal(rb.nbr_up.cpu().numpy(), nu)
 
 
+@pytest.mark.parametrize("case", ["subm3_indoor", "down_up"])
+def test_row_order_is_stable_mask_sort(cuda_lib, case):
+    """pv2_rulebook_row_order == numpy stable argsort of the neighbour-presence masks (bit-exact), and is a permutation."""
+    import ponderv2_b200.spconv.pytorch as spconv
+    ind, shape = _indoor_indices(7000, 77)
+    ind_t = torch.from_numpy(ind).to(_dev())
+    if case == "subm3_indoor":
+        maps = [spconv.build_subm_rulebook(ind_t, shape, 3).nbr]
+    else:
+        d = spconv.build_down_rulebook(ind_t, shape)
+        maps = [d.nbr_down, d.nbr_up]
+    for nbr in maps:
+        order = spconv.build_row_order(nbr).cpu().numpy()
+        m = nbr.cpu().numpy() >= 0
+        mask = np.zeros(m.shape[1], np.int64)
+        for k in range(m.shape[0]):
+            mask |= m[k].astype(np.int64) << k
+        want = np.argsort(mask, kind="stable").astype(np.int32)
+        assert np.array_equal(order, want)
+    assert spconv.build_row_order(torch.zeros((125, 10), dtype=torch.int32, device=_dev())) is None  # K > 32: no order
+
+
 def test_make_indices(cuda_lib):
     from ponderv2_b200.backbone import make_sparse_indices
     gc = torch.randint(0, 50, (1000, 3), dtype=torch.int64)
