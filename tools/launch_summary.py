@@ -8,6 +8,8 @@ with open(path) as f:
 agg = collections.defaultdict(lambda: [0, 0.0])
 n = 0
 for row in csv.DictReader(lines):
+    if row.get("Metric Name", "gpu__time_duration.sum") != "gpu__time_duration.sum":
+        continue
     try:
         v = float(row["Metric Value"].replace(",", ""))
     except (KeyError, ValueError):
