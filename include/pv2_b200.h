@@ -76,10 +76,13 @@ int pv2_rulebook_down_maps(const int32_t* in2out, const int32_t* koff, int64_t n
 /* Tile order for the sparse-conv kernels: order[pos] = row, rows sorted (stably) by their neighbour-presence mask
  * mask[j] = OR_k (nbr[k][j] >= 0) << k, so that a 128-row tile touches few distinct offsets and the (tile, offset)
  * pairs without any neighbour can be skipped (what spconv's implicit-GEMM mask sort does).  kvol <= 32, else
- * PV2_EUNSUPPORTED.  Convolution results never depend on the order. */
+ * PV2_EUNSUPPORTED.  Convolution results never depend on the order.
+ * Optional outputs (may be NULL): nbr_sorted [kvol, n] = the map in tile order, nbr_sorted[k][pos] = nbr[k][order[pos]]
+ * (what the conv kernels take together with `order`); blk_active [kvol, ceil(n/32)] = 1 iff any of the 32 consecutive
+ * tile-order rows of a block has a neighbour at offset k (the weight-gradient kernel skips the other blocks). */
 size_t pv2_rulebook_row_order_workspace_bytes(int64_t n);
-int pv2_rulebook_row_order(const int32_t* nbr, int64_t n, int kvol, int32_t* order,
-                           void* workspace, size_t workspace_bytes, void* stream);
+int pv2_rulebook_row_order(const int32_t* nbr, int64_t n, int kvol, int32_t* order, int32_t* nbr_sorted,
+                           uint8_t* blk_active, void* workspace, size_t workspace_bytes, void* stream);
 
 /* batch ids from cumulative offsets (ponder/models/utils.py:11-26 offset2batch) fused with the
  * [n,4] int32 (batch, c0, c1, c2) assembly of spconv_unet_v1m1_base.py:247-256.
@@ -95,7 +98,9 @@ int pv2_make_indices(const int64_t* grid_coord, const int64_t* offset, int64_t n
  * entry point serves forward (spconv layout [Cout,K,Cin]: strides K*Cin, Cin) and dgrad
  * (the transposed/k-flipped copy the host shim prepares).
  * ------------------------------------------------------------------------------------------ */
-/* row_order (optional, may be NULL): [n_out] permutation from pv2_rulebook_row_order grouping the output rows into tiles. */
+/* row_order (optional, may be NULL): [n_out] permutation from pv2_rulebook_row_order grouping the output rows into
+ * 128-row tiles.  When it is given, `nbr` must be the map IN TILE ORDER (pv2_rulebook_row_order's nbr_sorted):
+ * nbr[k][pos] is the input row feeding output row row_order[pos]. */
 int pv2_spconv_gather_gemm(const void* x, const void* w, int64_t w_stride_co, int64_t w_stride_k,
                            const float* bias, const int32_t* nbr, const int32_t* row_order, void* y,
                            int64_t n_in, int64_t n_out, int cin, int cout, int kvol,
@@ -106,7 +111,9 @@ size_t pv2_spconv_workspace_bytes(int64_t n_in, int cin, int cout, int kvol, int
 
 /* dw[co, k, ci] (+)= sum_j dy[j, co] * x[nbr[k][j], ci];  dw is float32 [Cout, K, Cin], must be
  * zeroed by the caller (accumulated with atomics across row chunks). */
-int pv2_spconv_wgrad(const void* x, const void* dy, const int32_t* nbr, const int32_t* row_order, float* dw,
+/* row_order / nbr as for pv2_spconv_gather_gemm; blk_active (optional) from pv2_rulebook_row_order. */
+int pv2_spconv_wgrad(const void* x, const void* dy, const int32_t* nbr, const int32_t* row_order,
+                     const uint8_t* blk_active, float* dw,
                      int64_t n_in, int64_t n_out, int cin, int cout, int kvol,
                      int dtype, void* workspace, size_t workspace_bytes, void* stream);
 /* scratch of the fp32 tensor-core weight-gradient kernel (split-precision copies of x and dy); without it the
@@ -188,6 +195,46 @@ int pv2_field_post_bwd(const float* vol, const float* pts, const float* dirs, in
 /* dvol[corner,c] += w dF[p,c] + [c<cs] (dw.gbar) u[p,c]   (u may be NULL) */
 int pv2_field_sample_bwd(const float* pts, const float* dF, int64_t dF_row, const float* u, const float* gbar,
                          int64_t P, int Z, int Y, int X, int C, int cs, float* dvol, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Per-ray kernels of the NeuS renderer (one warp per ray).  Replace the torch op chains of
+ * scene_colliders.py:38-99, ray_samplers.py:55-107,227-463, rays.py:83-153, sdf_field.py:122-146,
+ * renderers.py:5-75 and base_surface_model.py:102-211.  R rays, S0 coarse + Si importance samples, S = S0 + Si.
+ * ------------------------------------------------------------------------------------------ */
+/* AABB collider + stratified spacing bins [R,S0+1] + coarse points [R,S0,3].  noise: [R,noise_cols] uniform numbers
+ * (noise_cols = S0+1, or 1 for single_jitter) or NULL (eval: no jitter).  bbox_host: 6 floats (min xyz, max xyz). */
+int pv2_ray_setup(const float* origins, const float* dirs, const float* noise, int noise_cols, int64_t R, int S0,
+                  const float* bbox_host, float near_plane, float* nears, float* fars, float* bins, float* pts,
+                  void* stream);
+/* NeuSSampler with one upsample step: fixed-inv_s alphas of the coarse sdf [R,S0] -> weights (init_weights [R,S0],
+ * optional) -> PDF resampling (noise [R,noise_cols], noise_cols = Si+1 or 1, NULL = bin centres) -> merge ->
+ * starts/deltas [R,S], sample points [R,S,3] (normalised by 1+norm_padding+1e-3 when norm_pts), new_bins [R,Si]
+ * (optional), minmax[2] = float bits of the global min / max of starts.  S0 <= 128, Si <= 63. */
+int pv2_ray_resample(const float* origins, const float* dirs, const float* nears, const float* fars, const float* bins,
+                     const float* sdf, const float* noise, int noise_cols, int64_t R, int S0, int Si, float inv_s,
+                     int norm_pts, float norm_padding, float* starts, float* deltas, float* pts_norm, float* init_weights,
+                     float* new_bins, int32_t* minmax, void* stream);
+/* NeuS alpha -> transmittance -> weights [R,S] -> rgb [R,3] (rgbs/rgb may both be NULL), depth [R] (clipped to the
+ * global start range), normal [R,3].  variance: device float[1] (inv_s = clip(exp(10 v), 1e-6, 1e6)).  S <= 256. */
+int pv2_ray_composite_fwd(const float* sdf, const float* grad, const float* rgbs, const float* starts,
+                          const float* deltas, const float* dirs, const float* variance, const int32_t* minmax,
+                          float cos_anneal, int64_t R, int S, int clamp_rgb, float* weights, float* rgb, float* depth,
+                          float* normal, void* stream);
+/* g_rgb [R,3], g_depth [R], g_normal [R,3], g_weights [R,S] may each be NULL; g_variance [1] is accumulated (zero it). */
+int pv2_ray_composite_bwd(const float* sdf, const float* grad, const float* rgbs, const float* starts,
+                          const float* deltas, const float* dirs, const float* variance, const int32_t* minmax,
+                          float cos_anneal, int64_t R, int S, const float* g_rgb, const float* g_depth,
+                          const float* g_normal, const float* g_weights, float* g_sdf, float* g_grad, float* g_rgbs,
+                          float* g_variance, void* stream);
+/* Loss partial sums (zeroed here): sums[0..4] = numerators of depth-L1, rgb-L1, free-space, sdf, eikonal;
+ * sums[5..9] = counts n_valid, 0, n_front, n_sdf_mask, 0; sums[10] = sum of squared rgb error. */
+int pv2_ray_loss_fwd(const float* depth_pred, const float* rgb_pred, const float* depth_gt, const float* rgb_gt,
+                     const float* sdf, const float* z, const float* grad, int64_t R, int S, float trunc, float* sums,
+                     void* stream);
+/* gradients of sum_k coef[k] * numerator_k (coef: device float[5]) w.r.t. depth_pred, rgb_pred, sdf, grad */
+int pv2_ray_loss_bwd(const float* depth_pred, const float* rgb_pred, const float* depth_gt, const float* rgb_gt,
+                     const float* sdf, const float* z, const float* grad, int64_t R, int S, float trunc,
+                     const float* coef, float* g_depth, float* g_rgb, float* g_sdf, float* g_grad, void* stream);
 
 #ifdef __cplusplus
 }

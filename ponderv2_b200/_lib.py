@@ -30,11 +30,11 @@ SIGNATURES = {
     "pv2_rulebook_down_maps": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp]),
     "pv2_make_indices": (_int, [_vp, _vp, _i64, _int, _vp, _vp]),
     "pv2_rulebook_row_order_workspace_bytes": (_sz, [_i64]),
-    "pv2_rulebook_row_order": (_int, [_vp, _i64, _int, _vp, _vp, _sz, _vp]),
+    "pv2_rulebook_row_order": (_int, [_vp, _i64, _int, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pv2_spconv_gather_gemm": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _i64, _int, _int, _int, _int, _vp,
                                        _sz, _vp]),
     "pv2_spconv_workspace_bytes": (_sz, [_i64, _int, _int, _int, _int]),
-    "pv2_spconv_wgrad": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _int, _int, _int, _int, _vp, _sz, _vp]),
+    "pv2_spconv_wgrad": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _int, _int, _int, _int, _vp, _sz, _vp]),
     "pv2_wgrad_workspace_bytes": (_sz, [_i64, _i64, _int, _int]),
     "pv2_linear_workspace_bytes": (_sz, [_i64, _int, _int, _int]),
     "pv2_linear": (_int, [_vp, _i64, _i64, _int, _vp, _vp, _vp, _i64, _i64, _int, _int, _vp, _i64, _i64, _i64, _int, _int,
@@ -46,6 +46,15 @@ SIGNATURES = {
     "pv2_field_post_bwd": (_int, [_vp, _vp, _vp, _int, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _int,
                                    _int, _int, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "pv2_field_sample_bwd": (_int, [_vp, _vp, _i64, _vp, _vp, _i64, _int, _int, _int, _int, _int, _vp, _vp]),
+    "pv2_ray_setup": (_int, [_vp, _vp, _vp, _int, _i64, _int, C.POINTER(C.c_float), C.c_float, _vp, _vp, _vp, _vp, _vp]),
+    "pv2_ray_resample": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _i64, _int, _int, C.c_float, _int, C.c_float,
+                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pv2_ray_composite_fwd": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_float, _i64, _int, _int, _vp, _vp, _vp,
+                                      _vp, _vp]),
+    "pv2_ray_composite_bwd": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_float, _i64, _int, _vp, _vp, _vp, _vp,
+                                      _vp, _vp, _vp, _vp, _vp]),
+    "pv2_ray_loss_fwd": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, C.c_float, _vp, _vp]),
+    "pv2_ray_loss_bwd": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, C.c_float, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pv2_densify_fwd": (_int, [_vp, _vp, _i64, _int, _i64, _vp, _vp, _vp]),
     "pv2_densify_bwd": (_int, [_vp, _vp, _vp, _i64, _int, _vp, _vp]),
     "pv2_trilinear_fwd": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _int, _int, _int, _int, _vp]),

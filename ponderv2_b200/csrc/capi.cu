@@ -4,9 +4,10 @@
 
 extern "C" {
 
-int pv2_spconv_gather_gemm_simt(const void*, const void*, int64_t, int64_t, const float*, const int32_t*, void*, int64_t,
-                                int64_t, int, int, int, int, void*);
-int pv2_spconv_wgrad_simt(const void*, const void*, const int32_t*, float*, int64_t, int64_t, int, int, int, int, void*);
+int pv2_spconv_gather_gemm_simt(const void*, const void*, int64_t, int64_t, const float*, const int32_t*, const int32_t*,
+                                void*, int64_t, int64_t, int, int, int, int, void*);
+int pv2_spconv_wgrad_simt(const void*, const void*, const int32_t*, const int32_t*, float*, int64_t, int64_t, int, int, int,
+                          int, void*);
 
 static unsigned long long g_launches = 0;
 void pv2_note_launches(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
@@ -50,23 +51,25 @@ int pv2_spconv_gather_gemm(const void* x, const void* w, int64_t w_sco, int64_t 
                                          stream);
     if (rc != PV2_EUNSUPPORTED) return rc;
   }
-  return pv2_spconv_gather_gemm_simt(x, w, w_sco, w_sk, bias, nbr, y, n_in, n_out, cin, cout, kvol, dtype, stream);
+  return pv2_spconv_gather_gemm_simt(x, w, w_sco, w_sk, bias, nbr, row_order, y, n_in, n_out, cin, cout, kvol, dtype, stream);
 }
 
-int pv2_wgrad_umma(const float*, int64_t, int64_t, const float*, int64_t, int64_t, const int32_t*, const int32_t*, float*,
-                   int64_t, int64_t, int, int, int, void*, size_t, void*);
+int pv2_wgrad_umma(const float*, int64_t, int64_t, const float*, int64_t, int64_t, const int32_t*, const int32_t*,
+                   const uint8_t*, float*, int64_t, int64_t, int, int, int, void*, size_t, void*);
 
-int pv2_spconv_wgrad(const void* x, const void* dy, const int32_t* nbr, const int32_t* row_order, float* dw, int64_t n_in,
-                     int64_t n_out, int cin, int cout, int kvol, int dtype, void* workspace, size_t workspace_bytes,
-                     void* stream) {
+int pv2_spconv_wgrad(const void* x, const void* dy, const int32_t* nbr, const int32_t* row_order,
+                     const uint8_t* blk_active, float* dw, int64_t n_in, int64_t n_out, int cin, int cout, int kvol,
+                     int dtype, void* workspace, size_t workspace_bytes, void* stream) {
   // tensor-core wgrad pays off once the gathered rows are wide (measured on B200, 100 k voxels, K = 27:
   // 96->96 1.6 vs 2.4 ms, 256->256 6.4 vs 10.1 ms, but 32->32 1.1 vs 0.6 ms): narrow layers stay on the SIMT kernel
-  if (!force_simt() && dtype == PV2_F32 && kvol <= 32 && cin >= 96) {
-    int rc = pv2_wgrad_umma((const float*)x, cin, 0, (const float*)dy, cout, 0, nbr, row_order, dw, n_in, n_out, cin, cout,
-                            kvol, workspace, workspace_bytes, stream);
+  static int min_cin = -1;
+  if (min_cin < 0) { const char* e = getenv("PV2_WGRAD_UMMA_MIN_CIN"); min_cin = e ? atoi(e) : 32; }
+  if (!force_simt() && dtype == PV2_F32 && kvol <= 32 && cin >= min_cin) {
+    int rc = pv2_wgrad_umma((const float*)x, cin, 0, (const float*)dy, cout, 0, nbr, row_order, blk_active, dw, n_in, n_out,
+                            cin, cout, kvol, workspace, workspace_bytes, stream);
     if (rc != PV2_EUNSUPPORTED && rc != PV2_EWORKSPACE) return rc;
   }
-  return pv2_spconv_wgrad_simt(x, dy, nbr, dw, n_in, n_out, cin, cout, kvol, dtype, stream);
+  return pv2_spconv_wgrad_simt(x, dy, nbr, row_order, dw, n_in, n_out, cin, cout, kvol, dtype, stream);
 }
 
 }  // extern "C"

@@ -457,7 +457,7 @@ __global__ void __launch_bounds__(256) dense_wgrad_kernel(const float* __restric
 }  // namespace
 
 extern "C" int pv2_wgrad_umma(const float*, int64_t, int64_t, const float*, int64_t, int64_t, const int32_t*, const int32_t*,
-                              float*, int64_t, int64_t, int, int, int, void*, size_t, void*);
+                              const uint8_t*, float*, int64_t, int64_t, int, int, int, void*, size_t, void*);
 
 extern "C" int pv2_dense_wgrad(const float* x, int64_t x_row, int64_t x_lo_off, const float* dy, int64_t dy_row,
                                int64_t dy_lo_off, int64_t rows, int cin, int cout, float* dw, void* workspace,
@@ -465,7 +465,7 @@ extern "C" int pv2_dense_wgrad(const float* x, int64_t x_row, int64_t x_lo_off, 
   {
     const char* e = getenv("PV2_FORCE_SIMT");
     if (!(e && e[0] == '1') && cin >= 96) {
-      int rc = pv2_wgrad_umma(x, x_row, x_lo_off, dy, dy_row, dy_lo_off, nullptr, nullptr, dw, rows, rows, cin, cout, 1, workspace,
+      int rc = pv2_wgrad_umma(x, x_row, x_lo_off, dy, dy_row, dy_lo_off, nullptr, nullptr, nullptr, dw, rows, rows, cin, cout, 1, workspace,
                               workspace_bytes, stream_);
       if (rc != PV2_EUNSUPPORTED && rc != PV2_EWORKSPACE) return rc;
     }

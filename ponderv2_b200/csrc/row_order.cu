@@ -24,6 +24,26 @@ __global__ void row_mask_kernel(const int32_t* __restrict__ nbr, int64_t n, int 
   }
 }
 
+// nbr_sorted[k][pos] = nbr[k][order[pos]] (the map in tile order: coalesced for the conv kernels) and
+// blk_active[k][b] = 1 iff one of the 32 rows of block b has a neighbour at offset k (wgrad skips the other stages)
+__global__ void permute_map_kernel(const int32_t* __restrict__ nbr, const int32_t* __restrict__ order, int64_t n,
+                                   int kvol, int64_t nblk, int32_t* __restrict__ nbr_sorted,
+                                   uint8_t* __restrict__ blk_active) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t b = warp0; b < nblk; b += nwarps) {
+    const int64_t pos = b * 32 + lane;
+    const int64_t j = pos < n ? (int64_t)__ldg(&order[pos]) : -1;
+    for (int k = 0; k < kvol; ++k) {
+      const int32_t v = j >= 0 ? __ldg(&nbr[(int64_t)k * n + j]) : -1;
+      if (pos < n && nbr_sorted != nullptr) nbr_sorted[(int64_t)k * n + pos] = v;
+      const bool any = __any_sync(0xffffffffu, v >= 0);
+      if (lane == 0 && blk_active != nullptr) blk_active[(int64_t)k * nblk + b] = any ? 1 : 0;
+    }
+  }
+}
+
 inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 
 }  // namespace
@@ -32,12 +52,12 @@ extern "C" {
 
 size_t pv2_rulebook_row_order_workspace_bytes(int64_t n) {
   if (n < 0) return 0;
-  // mask in/out + iota + cub temporaries (histograms and per-tile look-back state: well under n/2 + 1 MiB bytes)
-  return 3 * align256((size_t)n * 4) + align256((size_t)n / 2 + (1u << 20));
+  // mask in/out + iota + cub temporaries (histograms + per-tile look-back state)
+  return 3 * align256((size_t)n * 4) + align256((size_t)n * 2 + (4u << 20));
 }
 
-int pv2_rulebook_row_order(const int32_t* nbr, int64_t n, int kvol, int32_t* order, void* workspace,
-                           size_t workspace_bytes, void* stream_) {
+int pv2_rulebook_row_order(const int32_t* nbr, int64_t n, int kvol, int32_t* order, int32_t* nbr_sorted,
+                           uint8_t* blk_active, void* workspace, size_t workspace_bytes, void* stream_) {
   PV2_CHECK_ARG(n >= 0 && kvol >= 1);
   if (kvol > 32) return PV2_EUNSUPPORTED;
   if (n == 0) return 0;
@@ -57,7 +77,13 @@ int pv2_rulebook_row_order(const int32_t* nbr, int64_t n, int kvol, int32_t* ord
   row_mask_kernel<<<pv2_grid_for(n, 256), 256, 0, stream>>>(nbr, n, kvol, mask_in, iota);
   e = cub::DeviceRadixSort::SortPairs(temp, temp_need, mask_in, mask_out, iota, order, (int)n, 0, kvol, stream);
   if (e != cudaSuccess) return (int)e;
-  PV2_DONE(2);
+  int launches = 2;
+  if (nbr_sorted != nullptr || blk_active != nullptr) {
+    const int64_t nblk = (n + 31) / 32;
+    permute_map_kernel<<<pv2_grid_for(nblk * 32, 256), 256, 0, stream>>>(nbr, order, n, kvol, nblk, nbr_sorted, blk_active);
+    ++launches;
+  }
+  PV2_DONE(launches);
 }
 
 }  // extern "C"

@@ -27,7 +27,8 @@ template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(flo
 template <typename T>
 __global__ void __launch_bounds__(256) gather_gemm_kernel(const T* __restrict__ x, const T* __restrict__ w,
                                                           int64_t w_sco, int64_t w_sk, const float* __restrict__ bias,
-                                                          const int32_t* __restrict__ nbr, T* __restrict__ y,
+                                                          const int32_t* __restrict__ nbr,
+                                                          const int32_t* __restrict__ order, T* __restrict__ y,
                                                           int64_t n_out, int cin, int cout, int kvol) {
   __shared__ float Xs[KC][TM + PAD];
   __shared__ float Ws[KC][TN + PAD];
@@ -99,6 +100,7 @@ __global__ void __launch_bounds__(256) gather_gemm_kernel(const T* __restrict__ 
   for (int i = 0; i < 4; ++i) {
     int64_t j = row0 + tr + i;
     if (j >= n_out) continue;
+    if (order != nullptr) j = __ldg(&order[j]);   // nbr is in tile order: position -> output row
 #pragma unroll
     for (int jx = 0; jx < 4; ++jx) {
       int co = col0 + tc + jx;
@@ -114,7 +116,8 @@ __global__ void __launch_bounds__(256) gather_gemm_kernel(const T* __restrict__ 
 // grid: x = row chunk, y = k, z = (co tile, ci tile)
 template <typename T>
 __global__ void __launch_bounds__(256) wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dy,
-                                                    const int32_t* __restrict__ nbr, float* __restrict__ dw,
+                                                    const int32_t* __restrict__ nbr,
+                                                    const int32_t* __restrict__ order, float* __restrict__ dw,
                                                     int64_t n_out, int cin, int cout, int kvol, int64_t rows_per_chunk,
                                                     int ci_tiles) {
   constexpr int RC = 16;  // rows per smem pass
@@ -153,6 +156,7 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const T* __restrict__ x, con
     {
       int64_t j = r0 + lr;
       int32_t src = rows_s[lr];
+      if (order != nullptr && src >= 0) j = __ldg(&order[j]);   // nbr is in tile order: position -> dy row
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         int co = co0 + lc + e, ci = ci0 + lc + e;
@@ -196,24 +200,24 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const T* __restrict__ x, con
 extern "C" {
 
 int pv2_spconv_gather_gemm_simt(const void* x, const void* w, int64_t w_sco, int64_t w_sk, const float* bias,
-                                const int32_t* nbr, void* y, int64_t n_in, int64_t n_out, int cin, int cout, int kvol,
-                                int dtype, void* stream_) {
+                                const int32_t* nbr, const int32_t* order, void* y, int64_t n_in, int64_t n_out, int cin,
+                                int cout, int kvol, int dtype, void* stream_) {
   PV2_CHECK_ARG(n_in >= 0 && n_out >= 0 && cin > 0 && cout > 0 && kvol > 0);
   if (n_out == 0) return 0;
   PV2_CHECK_ARG(x && w && nbr && y);
   cudaStream_t stream = (cudaStream_t)stream_;
   dim3 grid((unsigned)((n_out + TM - 1) / TM), (unsigned)((cout + TN - 1) / TN));
   if (dtype == PV2_F32)
-    gather_gemm_kernel<float><<<grid, 256, 0, stream>>>((const float*)x, (const float*)w, w_sco, w_sk, bias, nbr, (float*)y, n_out, cin, cout, kvol);
+    gather_gemm_kernel<float><<<grid, 256, 0, stream>>>((const float*)x, (const float*)w, w_sco, w_sk, bias, nbr, order, (float*)y, n_out, cin, cout, kvol);
   else if (dtype == PV2_BF16)
-    gather_gemm_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)w, w_sco, w_sk, bias, nbr, (__nv_bfloat16*)y, n_out, cin, cout, kvol);
+    gather_gemm_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)w, w_sco, w_sk, bias, nbr, order, (__nv_bfloat16*)y, n_out, cin, cout, kvol);
   else
     return PV2_EUNSUPPORTED;
   PV2_DONE(1);
 }
 
-int pv2_spconv_wgrad_simt(const void* x, const void* dy, const int32_t* nbr, float* dw, int64_t n_in, int64_t n_out,
-                          int cin, int cout, int kvol, int dtype, void* stream_) {
+int pv2_spconv_wgrad_simt(const void* x, const void* dy, const int32_t* nbr, const int32_t* order, float* dw, int64_t n_in,
+                          int64_t n_out, int cin, int cout, int kvol, int dtype, void* stream_) {
   PV2_CHECK_ARG(n_in >= 0 && n_out >= 0 && cin > 0 && cout > 0 && kvol > 0);
   if (n_out == 0) return 0;
   PV2_CHECK_ARG(x && dy && nbr && dw);
@@ -229,9 +233,9 @@ int pv2_spconv_wgrad_simt(const void* x, const void* dy, const int32_t* nbr, flo
   chunks = (n_out + rows_per_chunk - 1) / rows_per_chunk;
   dim3 grid((unsigned)chunks, (unsigned)kvol, (unsigned)(co_tiles * ci_tiles));
   if (dtype == PV2_F32)
-    wgrad_kernel<float><<<grid, 256, 0, stream>>>((const float*)x, (const float*)dy, nbr, dw, n_out, cin, cout, kvol, rows_per_chunk, ci_tiles);
+    wgrad_kernel<float><<<grid, 256, 0, stream>>>((const float*)x, (const float*)dy, nbr, order, dw, n_out, cin, cout, kvol, rows_per_chunk, ci_tiles);
   else if (dtype == PV2_BF16)
-    wgrad_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, nbr, dw, n_out, cin, cout, kvol, rows_per_chunk, ci_tiles);
+    wgrad_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, nbr, order, dw, n_out, cin, cout, kvol, rows_per_chunk, ci_tiles);
   else
     return PV2_EUNSUPPORTED;
   PV2_DONE(1);

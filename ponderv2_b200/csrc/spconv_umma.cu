@@ -4,7 +4,8 @@
 //                                                         reference call sites spconv_unet_v1m1_base.py:47-66,135-177)
 //
 // One CTA owns a tile of 128 output rows and all Cout (<= 256) columns.  Which rows form a tile is given by an optional
-// `order` permutation (rows with equal neighbour masks adjacent, pv2_rulebook_row_order): a (tile, offset) pair in which
+// `order` permutation (rows with equal neighbour masks adjacent, pv2_rulebook_row_order; `nbr` is then the map in tile
+// order, so the 128 indices of an offset are one coalesced line): a (tile, offset) pair in which
 // no row has a neighbour is skipped by every role, so mask-sorted tiles run ~K_present instead of K offsets.
 // The contraction runs over the concatenated axis (kernel offset k, input channel ci) in chunks of 128 bytes per row:
 //   * warps 0-7 are producers.  bf16: all 256 threads issue 16-byte cp.async (LDGSTS, zero-fill for missing neighbours)
@@ -94,7 +95,9 @@ __device__ __forceinline__ void split_store(uint32_t addr, uint32_t lo_delta, co
   st_shared_v4(addr + lo_delta, l);
 }
 
-template <bool kSplit>
+// kPre (fp32 only): x is stored split-precision (value = x[..] + x[.. + x_lo_off]); a template parameter because a
+// predicated-off FADD on a just-loaded register still waits for the load, which serialises the gather.
+template <bool kSplit, bool kPre>
 __global__ void __launch_bounds__(kThreads) umma_gather_gemm_kernel(const GGParams p) {
   using T = ModeTraits<kSplit>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -143,10 +146,27 @@ __global__ void __launch_bounds__(kThreads) umma_gather_gemm_kernel(const GGPara
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  for (int i = tid; i < p.kvol * kTileM; i += kThreads) {
-    const int k = i >> 7, r = i & (kTileM - 1);
-    const int32_t j = row_s[r];
-    idx_s[i] = (j >= 0) ? (p.nbr != nullptr ? __ldg(&p.nbr[(int64_t)k * p.n_out + j]) : j) : -1;
+  // neighbour indices of the tile (nbr is in tile order: 128 consecutive entries per offset, coalesced); loads are
+  // issued in batches of 6 before the first store waits
+  {
+    const int total = p.kvol * kTileM;
+    for (int i0 = tid; i0 < total; i0 += 6 * kThreads) {
+      int32_t v[6];
+#pragma unroll
+      for (int u = 0; u < 6; ++u) {
+        const int i = i0 + u * kThreads;
+        v[u] = -1;
+        if (i < total) {
+          const int64_t pos = row0 + (i & (kTileM - 1));
+          if (pos < p.n_out) v[u] = (p.nbr != nullptr) ? __ldg(&p.nbr[(int64_t)(i >> 7) * p.n_out + pos]) : (int32_t)pos;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 6; ++u) {
+        const int i = i0 + u * kThreads;
+        if (i < total) idx_s[i] = v[u];
+      }
+    }
   }
   __syncthreads();
   // which kernel offsets have at least one neighbour in this tile
@@ -236,11 +256,18 @@ __global__ void __launch_bounds__(kThreads) umma_gather_gemm_kernel(const GGPara
           if (src >= 0) {
             const float* g = x + ((int64_t)src * p.x_row + ci);
             va[i] = __ldg(reinterpret_cast<const float4*>(g));
-            if (p.x_lo_off != 0) {
-              const float4 l = __ldg(reinterpret_cast<const float4*>(g + p.x_lo_off));
-              va[i].x += l.x; va[i].y += l.y; va[i].z += l.z; va[i].w += l.w;
-            }
           }
+        }
+        if constexpr (kPre) {   // split-precision input: add the lo halves (second batch of loads, then the adds)
+          float4 vl[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int32_t src = kvalid ? idx_k[rbase + 16 * i] : -1;
+            vl[i] = zero4;
+            if (src >= 0) vl[i] = __ldg(reinterpret_cast<const float4*>(x + ((int64_t)src * p.x_row + ci) + p.x_lo_off));
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { va[i].x += vl[i].x; va[i].y += vl[i].y; va[i].z += vl[i].z; va[i].w += vl[i].w; }
         }
         const float* wk = w + ((int64_t)k * p.w_sk + ci);
         float4 vb[8];
@@ -456,7 +483,7 @@ __global__ void __launch_bounds__(kThreads) umma_gather_gemm_kernel(const GGPara
   }
 }
 
-template <bool kSplit>
+template <bool kSplit, bool kPre>
 int launch(const GGParams& p0, cudaStream_t stream) {
   using T = ModeTraits<kSplit>;
   GGParams p = p0;
@@ -473,7 +500,7 @@ int launch(const GGParams& p0, cudaStream_t stream) {
   const size_t smem = (size_t)stages * stage_bytes + fixed;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(umma_gather_gemm_kernel<kSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(umma_gather_gemm_kernel<kSplit, kPre>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          227 * 1024);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
@@ -492,7 +519,7 @@ int launch(const GGParams& p0, cudaStream_t stream) {
     ++launches;
   }
   dim3 grid(tiles, (unsigned)ksplit);
-  umma_gather_gemm_kernel<kSplit><<<grid, kThreads, smem, stream>>>(p);
+  umma_gather_gemm_kernel<kSplit, kPre><<<grid, kThreads, smem, stream>>>(p);
   PV2_DONE(launches);
 }
 
@@ -523,7 +550,7 @@ int pv2_spconv_gather_gemm_umma(const void* x, const void* w, int64_t w_sco, int
   p.x_row = cin; p.x_lo_off = 0;
   p.y_row = cout; p.y_lo_off = 0; p.y_split = 0; p.act = 0; p.y2 = nullptr; p.y2_row = 0; p.y2_lo_off = 0;
   cudaStream_t stream = (cudaStream_t)stream_;
-  return dtype == PV2_BF16 ? launch<false>(p, stream) : launch<true>(p, stream);
+  return dtype == PV2_BF16 ? launch<false, false>(p, stream) : launch<true, false>(p, stream);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -553,7 +580,7 @@ int pv2_linear(const float* x, int64_t x_row, int64_t x_lo_off, int x_presplit, 
   p.bias = bias; p.nbr = nullptr; p.order = nullptr; p.y = y; p.n_out = rows; p.cin = cin; p.cout = cout; p.kvol = 1;
   p.y_row = y_row; p.y_lo_off = y_lo_off; p.y_split = y_split; p.act = act;
   p.y2 = y2; p.y2_row = y2_row; p.y2_lo_off = y2_lo_off;
-  return launch<true>(p, (cudaStream_t)stream_);
+  return x_presplit ? launch<true, true>(p, (cudaStream_t)stream_) : launch<true, false>(p, (cudaStream_t)stream_);
 }
 
 }  // extern "C"

@@ -31,8 +31,9 @@ struct WGParams {
   int64_t x_row, x_lo;
   const float* dyt;    // transposed split dy: [2][cout][np]  (hi plane, lo plane)
   int64_t np;          // padded row count (multiple of 32) = row length of dyt
-  const int32_t* nbr;  // [kvol][n_out] or nullptr (identity, kvol = 1)
+  const int32_t* nbr;  // [kvol][n_out] in tile order (nbr[k][pos] feeds output row order[pos]) or nullptr (identity)
   const int32_t* order;  // optional [n_out]: position -> row (mask-sorted, pv2_rulebook_row_order); dyt is in this order
+  const uint8_t* blk_active;  // optional [kvol][ceil(n_out/32)]: 1 iff the 32-row block has a pair at offset k
   int max_iters;       // rows_per_chunk / 32 (capacity of the active-stage list)
   float* dw;           // [cout][kvol][cin]
   int64_t n_out;
@@ -51,6 +52,9 @@ __device__ __forceinline__ void split_tf32_dev(float v, float& hi, float& lo) {
   lo = __uint_as_float(l);
 }
 
+// kPre: x is split-precision (value = x[..] + x[.. + x_lo]); a template parameter so that the plain path carries no
+// (predicated-off but still scoreboard-waiting) adds between its gather loads.
+template <bool kPre>
 __global__ void __launch_bounds__(kThreads) umma_wgrad_kernel(const WGParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -77,15 +81,17 @@ __global__ void __launch_bounds__(kThreads) umma_wgrad_kernel(const WGParams p) 
   // an offset are empty (a surface voxel has ~9 of 27 neighbours); they are skipped by producers and MMA issuer alike.
   int n_act = n_iters;
   if (p.nbr != nullptr) {
-    for (int st = warp; st < n_iters; st += kThreads / 32) {
-      const int64_t pos = r_begin + (int64_t)st * kRowsPerStage + lane;
-      int32_t src = -1;
-      if (pos < r_end) {
-        const int64_t j = (p.order != nullptr) ? (int64_t)__ldg(&p.order[pos]) : pos;
-        src = __ldg(&p.nbr[(int64_t)k * p.n_out + j]);
+    if (p.blk_active != nullptr) {   // precomputed per rulebook: one coalesced byte per stage
+      const int64_t nblk = (p.n_out + kRowsPerStage - 1) / kRowsPerStage;
+      const uint8_t* ba = p.blk_active + (int64_t)k * nblk + r_begin / kRowsPerStage;
+      for (int st = tid; st < n_iters; st += kThreads) flag_s[st] = __ldg(&ba[st]);
+    } else {
+      for (int st = warp; st < n_iters; st += kThreads / 32) {
+        const int64_t pos = r_begin + (int64_t)st * kRowsPerStage + lane;
+        const int32_t src = (pos < r_end) ? __ldg(&p.nbr[(int64_t)k * p.n_out + pos]) : -1;
+        const bool any = __any_sync(0xffffffffu, src >= 0);
+        if (lane == 0) flag_s[st] = any ? 1 : 0;
       }
-      const bool any = __any_sync(0xffffffffu, src >= 0);
-      if (lane == 0) flag_s[st] = any ? 1 : 0;
     }
     __syncthreads();
     if (warp == 0) {
@@ -131,33 +137,40 @@ __global__ void __launch_bounds__(kThreads) umma_wgrad_kernel(const WGParams p) 
       if (it >= n_act) return -1;
       const int64_t pos = r_begin + (int64_t)stage_at(it) * kRowsPerStage + lane;
       if (pos >= r_end) return -1;
-      if (p.nbr == nullptr) return (int32_t)pos;
-      const int64_t j = (p.order != nullptr) ? (int64_t)__ldg(&p.order[pos]) : pos;
-      return __ldg(&p.nbr[(int64_t)k * p.n_out + j]);
+      return (p.nbr != nullptr) ? __ldg(&p.nbr[(int64_t)k * p.n_out + pos]) : (int32_t)pos;
     };
-    int32_t src_next = load_src(0);
+    // B operand rows travel global -> registers -> (split, transposed) shared memory.  The loads of stage it + 1 are
+    // issued before stage it is split and stored (register double buffer) and the neighbour index is fetched two stages
+    // ahead, so one gather is always in flight per warp.
+    auto load_rows = [&](int32_t src, float4 (&xv)[kMaxUnitsPerWarp]) {
+      const float* xr = p.x + (int64_t)(src >= 0 ? src : 0) * p.x_row;
+#pragma unroll
+      for (int q = 0; q < kMaxUnitsPerWarp; ++q) {
+        const int u = warp * upw + q;   // each lane reads one contiguous run of its row (whole sectors, fetched once)
+        xv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (q < upw && src >= 0 && u * 4 < p.cin) xv[q] = __ldg(reinterpret_cast<const float4*>(xr) + u);
+      }
+      if constexpr (kPre) {
+        float4 xl[kMaxUnitsPerWarp];
+#pragma unroll
+        for (int q = 0; q < kMaxUnitsPerWarp; ++q) {
+          const int u = warp * upw + q;
+          xl[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (q < upw && src >= 0 && u * 4 < p.cin) xl[q] = __ldg(reinterpret_cast<const float4*>(xr + p.x_lo) + u);
+        }
+#pragma unroll
+        for (int q = 0; q < kMaxUnitsPerWarp; ++q) { xv[q].x += xl[q].x; xv[q].y += xl[q].y; xv[q].z += xl[q].z; xv[q].w += xl[q].w; }
+      }
+    };
+    float4 xcur[kMaxUnitsPerWarp], xnext[kMaxUnitsPerWarp];
+    load_rows(load_src(0), xcur);
+    int32_t src_next = load_src(1);
     for (int it = 0; it < n_act + lag; ++it) {
       if (it < n_act) {
         const int s = it % p.stages;
         const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-        // B operand: every global load of this stage is issued before anything waits (latency overlaps the barrier wait
-        // and the A copies); the neighbour index of the next stage is prefetched as well
-        const int32_t src = src_next;
-        const float* xr = p.x + (int64_t)(src >= 0 ? src : 0) * p.x_row;
-        float4 xv[kMaxUnitsPerWarp];
-#pragma unroll
-        for (int q = 0; q < kMaxUnitsPerWarp; ++q) {
-          const int u = warp * upw + q;   // each lane reads one contiguous run of its row (whole sectors, fetched once)
-          xv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (q < upw && src >= 0 && u * 4 < p.cin) {
-            xv[q] = __ldg(reinterpret_cast<const float4*>(xr) + u);
-            if (p.x_lo) {
-              const float4 w = __ldg(reinterpret_cast<const float4*>(xr + p.x_lo) + u);
-              xv[q].x += w.x; xv[q].y += w.y; xv[q].z += w.z; xv[q].w += w.w;
-            }
-          }
-        }
-        src_next = load_src(it + 1);
+        load_rows(src_next, xnext);          // stage it + 1 (all zeros past the end)
+        src_next = load_src(it + 2);
         mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
         uint8_t* a_hi = smem + (size_t)s * stage_bytes;
         uint8_t* b_hi = a_hi + 2 * kABytes;
@@ -175,9 +188,9 @@ __global__ void __launch_bounds__(kThreads) umma_wgrad_kernel(const WGParams p) 
         // B: lane = row j; transposing stores (bank = f(lane) only -> conflict-free)
 #pragma unroll
         for (int q = 0; q < kMaxUnitsPerWarp; ++q) {
-          const int u = warp * upw + q;   // each lane reads one contiguous run of its row (whole sectors, fetched once)
+          const int u = warp * upw + q;
           if (q < upw) {
-            const float vv[4] = {xv[q].x, xv[q].y, xv[q].z, xv[q].w};
+            const float vv[4] = {xcur[q].x, xcur[q].y, xcur[q].z, xcur[q].w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               float h, l;
@@ -188,6 +201,8 @@ __global__ void __launch_bounds__(kThreads) umma_wgrad_kernel(const WGParams p) 
             }
           }
         }
+#pragma unroll
+        for (int q = 0; q < kMaxUnitsPerWarp; ++q) xcur[q] = xnext[q];
       }
       cp_async_commit();
       if (it >= lag) {
@@ -315,13 +330,16 @@ int launch_wgrad(WGParams p, cudaStream_t stream) {
   fixed += 3 * p.max_iters + 16;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(umma_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(umma_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(umma_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
   const size_t smem = (size_t)stages * stage_bytes + fixed;
   dim3 grid((unsigned)chunks, (unsigned)p.kvol, (unsigned)m_tiles);
-  umma_wgrad_kernel<<<grid, kThreads, smem, stream>>>(p);
+  if (p.x_lo != 0) umma_wgrad_kernel<true><<<grid, kThreads, smem, stream>>>(p);
+  else umma_wgrad_kernel<false><<<grid, kThreads, smem, stream>>>(p);
   PV2_DONE(1);
 }
 
@@ -339,7 +357,8 @@ size_t pv2_wgrad_workspace_bytes(int64_t n_in, int64_t n_out, int cin, int cout)
 // render MLP can hand over its split-precision activations directly.  Returns PV2_EUNSUPPORTED for shapes the
 // tensor-core kernel does not take (caller falls back to the SIMT kernel).
 int pv2_wgrad_umma(const float* x, int64_t x_row, int64_t x_lo, const float* dy, int64_t dy_row, int64_t dy_lo,
-                   const int32_t* nbr, const int32_t* order, float* dw, int64_t n_in, int64_t n_out, int cin, int cout, int kvol,
+                   const int32_t* nbr, const int32_t* order, const uint8_t* blk_active, float* dw, int64_t n_in,
+                   int64_t n_out, int cin, int cout, int kvol,
                    void* workspace, size_t workspace_bytes, void* stream_) {
   PV2_CHECK_ARG(n_in >= 0 && n_out >= 0 && cin > 0 && cout > 0 && kvol > 0);
   if (n_out == 0 || n_in == 0) return 0;
@@ -357,6 +376,7 @@ int pv2_wgrad_umma(const float* x, int64_t x_row, int64_t x_lo, const float* dy,
   pv2_note_launches(1);
   WGParams p{};
   p.x = x; p.x_row = x_row; p.x_lo = x_lo; p.dyt = dyt; p.np = np; p.nbr = nbr; p.order = (nbr != nullptr) ? order : nullptr;
+  p.blk_active = (nbr != nullptr) ? blk_active : nullptr;
   p.dw = dw;
   p.n_out = n_out; p.cin = cin; p.cout = cout; p.kvol = kvol;
   return launch_wgrad(p, stream);

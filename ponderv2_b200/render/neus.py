@@ -22,7 +22,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from ..smooth_sampler import SmoothSampler
-from . import fused
+from . import fused, ray
 
 
 class RayBundle:
@@ -288,6 +288,9 @@ class NeuSModel(nn.Module):
         # hand-derived tensor-core field (render/fused.py) whenever the configuration is the indoor one; the generic
         # autograd-through-the-sampler path otherwise.  Both are CUDA-only.
         self.use_fused = True
+        # per-ray CUDA kernels for collider / sampler / compositing / losses (render/ray.py); torch elementwise otherwise
+        self.use_ray_kernels = True
+        self._loss_consts = {}
 
     def forward(self, ray_bundle: RayBundle, volume_feature: List[torch.Tensor], noise: Optional[dict] = None,
                 **kwargs) -> Dict[str, torch.Tensor]:
@@ -302,6 +305,9 @@ class NeuSModel(nn.Module):
         R = rb.origins.shape[0]
         use_fused = (self.use_fused and fused.eligible(self.field) and len(volume_feature) == 1
                      and volume_feature[0].shape[0] == 128)
+        if use_fused and self.use_ray_kernels and ray.supported(smp.num_samples, smp.num_samples_importance,
+                                                                smp.num_upsample_steps):
+            return self._forward_ray_kernels(rb, volume_feature[0], noise)
         if use_fused:
             vol_cl = volume_feature[0].permute(1, 2, 3, 0).contiguous().float()  # free for channels_last_3d volumes
             fp = fused.fold_parameters(self.field)
@@ -370,8 +376,76 @@ class NeuSModel(nn.Module):
         out.update(weights=weights, sdf=fo["sdf"], gradients=fo["gradients"], z_vals=starts, sampled_points=pts)
         return out
 
+    def _forward_ray_kernels(self, rb: RayBundle, volume: torch.Tensor, noise: dict) -> Dict[str, torch.Tensor]:
+        """Indoor configuration, everything proportional to rays x samples in libpv2_b200: ray_setup -> coarse SDF
+        (tensor cores) -> ray_resample -> fused field (tensor cores, analytic gradient) -> ray_composite."""
+        smp, fld = self.sampler, self.field
+        o, d = rb.origins, rb.directions
+        R, S0, Si = o.shape[0], smp.num_samples, smp.num_samples_importance
+        S = S0 + Si
+        jitter = smp.train_stratified and self.training
+        nz_u = nz_p = None
+        if jitter:
+            nz_u = noise.get("uniform")
+            if nz_u is None:
+                nz_u = torch.rand((R, 1 if smp.single_jitter else S0 + 1), dtype=torch.float32, device=o.device)
+            nz_p = noise.get("pdf")
+            if nz_p is None:
+                nz_p = torch.rand((R, 1 if smp.single_jitter else Si + 1), dtype=torch.float32, device=o.device)
+        vol_cl = volume.permute(1, 2, 3, 0).contiguous().float()   # free for channels_last_3d volumes
+        fp = fused.fold_parameters(fld)
+        nears, fars, bins, pts_c = ray.ray_setup(o, d, S0, self.collider.bbox, self.collider.near_plane, nz_u)
+        rb.nears, rb.fars = nears, fars
+        with torch.no_grad():
+            sdf_c = fused.coarse_sdf(vol_cl.detach(), pts_c.view(-1, 3), fp["M0"].detach(), fp["c0"].detach(),
+                                     fp["wcat"][:4].detach().contiguous(), fp["c1"][:4].detach().contiguous())
+        starts, deltas, pn, init_w, new_bins, minmax = ray.ray_resample(
+            o, d, nears, fars, bins, sdf_c, Si, smp.base_variance, nz_p, fld.norm_pts, fld.norm_padding)
+        sdf_f, grad_f, rgb_f = fused.FusedFieldFunction.apply(
+            vol_cl, pn.view(-1, 3), d, S, fp["M0"], fp["c0"], fp["wcat"], fp["c1"], fp["wp"], fp["m10"], fp["Mr"],
+            fp["cr"])
+        sdf_f, grad_f, rgb_f = sdf_f.view(R, S), grad_f.view(R, S, 3), rgb_f.view(R, S, 3)
+        weights, rgb, depth, normal = ray.RayComposite.apply(
+            sdf_f, grad_f, rgb_f, fld.deviation_network.variance, starts, deltas, d, minmax, fld._cos_anneal_ratio,
+            not self.training)
+        o3, d3 = o[:, None, :], d[:, None, :]
+        z = starts[..., None]
+        new_e = new_bins * fars + (1 - new_bins) * nears
+        return dict(rgb=rgb, depth=depth[:, None], normal=normal, weights=weights[..., None], sdf=sdf_f[..., None],
+                    gradients=grad_f, z_vals=z, sampled_points=o3 + d3 * z, init_sampled_points=pts_c,
+                    init_weights=init_w[..., None], new_sampled_points=o3 + d3 * new_e[..., None])
+
+    def _fused_loss(self, preds_dict, targets):
+        lw = self.loss.weights
+        sdf, z, grad = preds_dict["sdf"][..., 0], preds_dict["z_vals"][..., 0], preds_dict["gradients"]
+        R, S = sdf.shape
+        rgb_gt = targets.get("rgb")
+        has_rgb = "rgb" in preds_dict and rgb_gt is not None and lw.get("rgb_loss", 0.0) > 0
+        wts = (float(lw.get("depth_loss", 0.0)), float(lw.get("rgb_loss", 0.0)) if has_rgb else 0.0,
+               float(lw.get("free_space_loss", 0.0)), float(lw.get("sdf_loss", 0.0)), float(lw.get("eikonal_loss", 0.0)))
+        key = (R, S, sdf.device, wts)
+        if key not in self._loss_consts:
+            self._loss_consts[key] = (torch.tensor(wts, dtype=torch.float32, device=sdf.device),
+                                      torch.tensor([1.0, 3.0 * R, 1.0, 1.0, float(R) * S], dtype=torch.float32,
+                                                   device=sdf.device))
+        wvec, const = self._loss_consts[key]
+        terms = ray.RayLoss.apply(preds_dict["depth"], preds_dict["rgb"] if has_rgb else None, sdf, grad, z,
+                                  targets["depth"], rgb_gt if has_rgb else None,
+                                  float(self.loss.sensor_depth_truncation), wvec, const)
+        ld = {}
+        for i, name in enumerate(("depth_loss", "rgb_loss", "free_space_loss", "sdf_loss", "eikonal_loss")):
+            if wts[i] > 0:
+                ld[name] = terms[i]
+        if has_rgb:
+            ld["psnr"] = 20.0 * torch.log10(1.0 / terms[5].sqrt())
+        return ld
+
     def get_loss(self, preds_dict, targets):
         lw = self.loss.weights
+        if lw.get("semantic_loss", 0.0) > 0:
+            raise NotImplementedError("semantic (CLIP) rendering loss is SURVEY §8(f) rank 4, not in this round")
+        if self.use_ray_kernels and preds_dict["sdf"].is_cuda and preds_dict["sdf"].dtype == torch.float32:
+            return self._fused_loss(preds_dict, targets)
         ld = {}
         depth_gt = targets["depth"]
         valid = depth_gt > 0.0

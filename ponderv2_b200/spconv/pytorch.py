@@ -38,31 +38,54 @@ __all__ = [
 # ----------------------------------------------------------------------------------------------
 # rulebooks
 # ----------------------------------------------------------------------------------------------
-def build_row_order(nbr: torch.Tensor) -> Optional[torch.Tensor]:
-    """order[pos] = row: rows sorted by neighbour-presence mask so that 128-row tiles touch few kernel offsets
-    (pv2_rulebook_row_order).  None for maps the tile-skipping kernels do not use (K > 32, empty)."""
+class TileMap:
+    """A neighbour map prepared for the conv kernels: `nbr` [K, n] (tile order when `order` is set: nbr[k][pos] feeds
+    output row order[pos]), `order` [n] int32 or None, `blk_active` [K, ceil(n/32)] uint8 or None."""
+
+    __slots__ = ("nbr", "order", "blk_active")
+
+    def __init__(self, nbr, order=None, blk_active=None):
+        self.nbr, self.order, self.blk_active = nbr, order, blk_active
+
+
+def build_tile_map(nbr: torch.Tensor) -> TileMap:
+    """Rows sorted by neighbour-presence mask so that 128-row tiles touch few kernel offsets (pv2_rulebook_row_order),
+    the map permuted into that order, and the per-32-row-block activity bytes of the weight-gradient kernel.
+    Maps the tile-skipping kernels do not use (K > 32, K = 1, empty) stay in natural order."""
     kvol, n = nbr.shape
-    if kvol > 32 or kvol < 2 or n == 0:
-        return None
+    if not USE_ROW_ORDER or kvol > 32 or kvol < 2 or n == 0:
+        return TileMap(nbr)
     lib = _lib.load()
-    order = torch.empty(n, dtype=torch.int32, device=nbr.device)
+    dev = nbr.device
+    order = torch.empty(n, dtype=torch.int32, device=dev)
+    nbr_sorted = torch.empty_like(nbr)
+    blk = torch.empty((kvol, (n + 31) // 32), dtype=torch.uint8, device=dev)
     ws_bytes = lib.pv2_rulebook_row_order_workspace_bytes(n)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=nbr.device)
-    with torch.cuda.device(nbr.device):
-        _lib.check(lib.pv2_rulebook_row_order(_lib.ptr(nbr), n, kvol, _lib.ptr(order), _lib.ptr(ws), ws_bytes,
-                                              _lib.stream_ptr()), "pv2_rulebook_row_order")
-    return order
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.pv2_rulebook_row_order(_lib.ptr(nbr), n, kvol, _lib.ptr(order), _lib.ptr(nbr_sorted),
+                                              _lib.ptr(blk), _lib.ptr(ws), ws_bytes, _lib.stream_ptr()),
+                   "pv2_rulebook_row_order")
+    return TileMap(nbr_sorted, order, blk)
+
+
+def build_row_order(nbr: torch.Tensor) -> Optional[torch.Tensor]:
+    """order[pos] = row (stable sort of the rows by neighbour-presence mask), or None when no order is used."""
+    return build_tile_map(nbr).order
 
 
 class SubMRulebook:
     """nbr[k][j] = input row feeding output row j through kernel offset k, or -1; `order` groups rows into tiles."""
 
-    def __init__(self, nbr: torch.Tensor, ksize: int, pair_count: Optional[torch.Tensor],
-                 order: Optional[torch.Tensor] = None):
-        self.nbr = nbr
+    def __init__(self, nbr: torch.Tensor, ksize: int, pair_count: Optional[torch.Tensor]):
+        self.nbr = nbr                    # canonical map [K, n] (natural row order; what the parity tests compare)
         self.ksize = ksize
         self._pair_count = pair_count
-        self.order = order
+        self.tmap = build_tile_map(nbr)   # what the kernels consume
+
+    @property
+    def order(self):
+        return self.tmap.order
 
     @property
     def num_pairs(self) -> int:
@@ -81,8 +104,8 @@ class DownRulebook:
         self.koff = koff
         self.nbr_down = nbr_down  # [8, n_out]
         self.nbr_up = nbr_up      # [8, n_in]
-        self.order_down = build_row_order(nbr_down)   # tile order of the coarse rows
-        self.order_up = build_row_order(nbr_up)       # tile order of the fine rows (one offset per row -> 8x fewer chunks)
+        self.tmap_down = build_tile_map(nbr_down)   # coarse rows as outputs
+        self.tmap_up = build_tile_map(nbr_up)       # fine rows as outputs (one offset per row -> 8x fewer chunks)
 
 
 def _check_indices(indices: torch.Tensor) -> None:
@@ -106,7 +129,7 @@ def build_subm_rulebook(indices: torch.Tensor, spatial_shape: Sequence[int], ksi
         _lib.check(lib.pv2_rulebook_subm(_lib.ptr(indices), n, _lib.i32x3(spatial_shape), ksize, _lib.ptr(nbr),
                                          _lib.ptr(pc), _lib.ptr(ws), ws_bytes, _lib.stream_ptr()),
                    "pv2_rulebook_subm")
-    return SubMRulebook(nbr, ksize, pc, build_row_order(nbr) if USE_ROW_ORDER else None)
+    return SubMRulebook(nbr, ksize, pc)
 
 
 def build_down_rulebook(indices: torch.Tensor, spatial_shape: Sequence[int]) -> DownRulebook:
@@ -137,10 +160,10 @@ def build_down_rulebook(indices: torch.Tensor, spatial_shape: Sequence[int]) -> 
 # ----------------------------------------------------------------------------------------------
 # arithmetic
 # ----------------------------------------------------------------------------------------------
-def _gather_gemm(x: torch.Tensor, w3: torch.Tensor, bias: Optional[torch.Tensor], nbr: torch.Tensor,
-                 n_out: int, order: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """y[j] = bias + sum_k w3[:, k, :] @ x[nbr[k][j]];  w3 is [Cout, K, Cin] (any strides with unit Cin stride).
-    `order` ([n_out] int32, optional) is the tile order of the output rows (build_row_order)."""
+def _gather_gemm(x: torch.Tensor, w3: torch.Tensor, bias: Optional[torch.Tensor], tmap: TileMap,
+                 n_out: int) -> torch.Tensor:
+    """y[j] = bias + sum_k w3[:, k, :] @ x[nbr[k][j]];  w3 is [Cout, K, Cin] (any strides with unit Cin stride)."""
+    nbr, order = tmap.nbr, tmap.order
     lib = _lib.load()
     cout, kvol, cin = w3.shape
     assert w3.stride(2) == 1
@@ -161,8 +184,8 @@ def _gather_gemm(x: torch.Tensor, w3: torch.Tensor, bias: Optional[torch.Tensor]
     return y
 
 
-def _wgrad(x: torch.Tensor, dy: torch.Tensor, nbr: torch.Tensor, kvol: int,
-           order: Optional[torch.Tensor] = None) -> torch.Tensor:
+def _wgrad(x: torch.Tensor, dy: torch.Tensor, tmap: TileMap, kvol: int) -> torch.Tensor:
+    nbr, order = tmap.nbr, tmap.order
     lib = _lib.load()
     cin, cout = x.shape[1], dy.shape[1]
     dw = torch.zeros((cout, kvol, cin), dtype=torch.float32, device=x.device)
@@ -172,7 +195,8 @@ def _wgrad(x: torch.Tensor, dy: torch.Tensor, nbr: torch.Tensor, kvol: int,
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes else None
     with torch.cuda.device(x.device), _lib.timed("pv2_spconv_wgrad", nbytes, 0):
         _lib.check(lib.pv2_spconv_wgrad(_lib.ptr(x.contiguous()), _lib.ptr(dy.contiguous()), _lib.ptr(nbr),
-                                        _lib.ptr(order), _lib.ptr(dw), x.shape[0], dy.shape[0], cin, cout, kvol,
+                                        _lib.ptr(order), _lib.ptr(tmap.blk_active), _lib.ptr(dw), x.shape[0],
+                                        dy.shape[0], cin, cout, kvol,
                                         _lib.dtype_code(x.dtype), _lib.ptr(ws), ws_bytes, _lib.stream_ptr()),
                    "pv2_spconv_wgrad")
     return dw
@@ -183,7 +207,7 @@ class _SparseConvFunction(torch.autograd.Function):
     `flip` mirrors the kernel offsets for the data gradient (submanifold symmetry: nbr[k][j]=i <=> nbr[K-1-k][i]=j)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, nbr_fwd, nbr_bwd, n_out: int, flip: bool, order_fwd=None, order_bwd=None):
+    def forward(ctx, x, weight, bias, map_fwd: TileMap, map_bwd: TileMap, n_out: int, flip: bool):
         cout, cin = weight.shape[0], weight.shape[-1]
         compute_dtype = x.dtype
         if torch.is_autocast_enabled():
@@ -193,9 +217,9 @@ class _SparseConvFunction(torch.autograd.Function):
         xc = x.to(compute_dtype)
         w3 = weight.reshape(cout, -1, cin).to(compute_dtype)
         b = bias.float() if bias is not None else None
-        y = _gather_gemm(xc, w3, b, nbr_fwd, n_out, order_fwd)
-        ctx.save_for_backward(xc, w3, nbr_fwd, nbr_bwd)
-        ctx.order_fwd, ctx.order_bwd = order_fwd, order_bwd
+        y = _gather_gemm(xc, w3, b, map_fwd, n_out)
+        ctx.save_for_backward(xc, w3)
+        ctx.map_fwd, ctx.map_bwd = map_fwd, map_bwd
         ctx.flip = flip
         ctx.has_bias = bias is not None
         ctx.weight_shape = weight.shape
@@ -205,18 +229,18 @@ class _SparseConvFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
-        xc, w3, nbr_fwd, nbr_bwd = ctx.saved_tensors
+        xc, w3 = ctx.saved_tensors
         dy = dy.contiguous().to(xc.dtype)
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             wt = w3.flip(1) if ctx.flip else w3
             wt = wt.permute(2, 1, 0).contiguous()  # [Cin, K, Cout]
-            dx = _gather_gemm(dy, wt, None, nbr_bwd, xc.shape[0], ctx.order_bwd).to(ctx.x_dtype)
+            dx = _gather_gemm(dy, wt, None, ctx.map_bwd, xc.shape[0]).to(ctx.x_dtype)
         if ctx.needs_input_grad[1]:
-            dw = _wgrad(xc, dy, nbr_fwd, w3.shape[1], ctx.order_fwd).reshape(ctx.weight_shape).to(ctx.weight_dtype)
+            dw = _wgrad(xc, dy, ctx.map_fwd, w3.shape[1]).reshape(ctx.weight_shape).to(ctx.weight_dtype)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = dy.float().sum(0)
-        return dx, dw, db, None, None, None, None, None, None
+        return dx, dw, db, None, None, None, None
 
 
 # ----------------------------------------------------------------------------------------------
@@ -380,7 +404,7 @@ class SubMConv3d(_SparseConvBase):
                     input.indice_dict[self.indice_key] = rb
             elif not isinstance(rb, SubMRulebook) or rb.ksize != ks[0] or rb.nbr.shape[1] != n:
                 raise ValueError(f"indice_key {self.indice_key!r} holds a rulebook of a different conv")
-        y = _SparseConvFunction.apply(input.features, self.weight, self.bias, rb.nbr, rb.nbr, n, True, rb.order, rb.order)
+        y = _SparseConvFunction.apply(input.features, self.weight, self.bias, rb.tmap, rb.tmap, n, True)
         return input.replace_feature(y)
 
 
@@ -394,8 +418,7 @@ class SparseConv3d(_SparseConvBase):
             if self.indice_key is not None:
                 input.indice_dict[self.indice_key] = rb
         n_out = rb.out_indices.shape[0]
-        y = _SparseConvFunction.apply(input.features, self.weight, self.bias, rb.nbr_down, rb.nbr_up, n_out, False,
-                                      rb.order_down if USE_ROW_ORDER else None, rb.order_up if USE_ROW_ORDER else None)
+        y = _SparseConvFunction.apply(input.features, self.weight, self.bias, rb.tmap_down, rb.tmap_up, n_out, False)
         return SparseConvTensor(y, rb.out_indices, rb.out_shape, input.batch_size, input.grid, input.voxel_num,
                                 input.indice_dict, input.benchmark)
 
@@ -411,7 +434,6 @@ class SparseInverseConv3d(_SparseConvBase):
         if self.kernel_size != [2, 2, 2]:
             raise NotImplementedError("SparseInverseConv3d: kernel_size=2 only")
         n_fine = rb.in_indices.shape[0]
-        y = _SparseConvFunction.apply(input.features, self.weight, self.bias, rb.nbr_up, rb.nbr_down, n_fine, False,
-                                      rb.order_up if USE_ROW_ORDER else None, rb.order_down if USE_ROW_ORDER else None)
+        y = _SparseConvFunction.apply(input.features, self.weight, self.bias, rb.tmap_up, rb.tmap_down, n_fine, False)
         return SparseConvTensor(y, rb.in_indices, rb.in_shape, input.batch_size, input.grid, input.voxel_num,
                                 input.indice_dict, input.benchmark)

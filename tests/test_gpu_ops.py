@@ -118,6 +118,13 @@ def test_row_order_is_stable_mask_sort(cuda_lib, case):
             mask |= m[k].astype(np.int64) << k
         want = np.argsort(mask, kind="stable").astype(np.int32)
         assert np.array_equal(order, want)
+        tm = spconv.build_tile_map(nbr)
+        nbr_np = nbr.cpu().numpy()
+        assert np.array_equal(tm.nbr.cpu().numpy(), nbr_np[:, want])            # the map in tile order
+        nblk = (nbr_np.shape[1] + 31) // 32
+        padded = np.full((nbr_np.shape[0], nblk * 32), -1, np.int32)
+        padded[:, :nbr_np.shape[1]] = nbr_np[:, want]
+        assert np.array_equal(tm.blk_active.cpu().numpy(), (padded.reshape(nbr_np.shape[0], nblk, 32) >= 0).any(2))
     assert spconv.build_row_order(torch.zeros((125, 10), dtype=torch.int32, device=_dev())) is None  # K > 32: no order
 
 

@@ -9,7 +9,9 @@ timeout 900 python -m pytest tests -m gpu -x -q > $out/${tag}_pytest.log 2>&1; e
 tail -15 $out/${tag}_pytest.log
 if [ "${SKIP_MICRO:-0}" != "1" ]; then
   timeout 600 python tools/spconv_microbench.py --levels --out $out/${tag}_micro_levels.json 2>&1 | tee $out/${tag}_micro_levels.txt
-  PV2_ROW_ORDER=0 timeout 600 python tools/spconv_microbench.py --levels 2>&1 | tee $out/${tag}_micro_levels_noorder.txt
+  if [ "${MICRO_NOORDER:-0}" = "1" ]; then
+    PV2_ROW_ORDER=0 timeout 600 python tools/spconv_microbench.py --levels 2>&1 | tee $out/${tag}_micro_levels_noorder.txt
+  fi
   timeout 600 python tools/spconv_microbench.py --sizes 100000,1000000 --out $out/${tag}_micro_c5.json 2>&1 | tee $out/${tag}_micro_c5.txt
 fi
 timeout 900 python bench.py --steps 10 --warmup 3 > $out/${tag}_bench.json 2> $out/${tag}_bench.log; echo "bench exit $?"

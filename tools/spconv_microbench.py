@@ -56,9 +56,9 @@ def bench_layer(rb, n, cin, cout, dtype, hbm):
     dy = torch.randn(n, cout, device=DEV).to(dtype)
     wt = w3.flip(1).permute(2, 1, 0).contiguous()
     P = rb.num_pairs
-    t_f = timed(lambda: sp._gather_gemm(x, w3, None, nbr, n, rb.order))
-    t_d = timed(lambda: sp._gather_gemm(dy, wt, None, nbr, n, rb.order))
-    t_w = timed(lambda: sp._wgrad(x, dy, nbr, K, rb.order))
+    t_f = timed(lambda: sp._gather_gemm(x, w3, None, rb.tmap, n))
+    t_d = timed(lambda: sp._gather_gemm(dy, wt, None, rb.tmap, n))
+    t_w = timed(lambda: sp._wgrad(x, dy, rb.tmap, K))
     by_f = n * cin * b + n * cout * b + K * cin * cout * b + 4 * K * n
     by_w = n * (cin + cout) * b + K * cin * cout * 4 + 4 * K * n
     fl = 2.0 * P * cin * cout
