@@ -75,8 +75,8 @@ int pv2_rulebook_down_maps(const int32_t* in2out, const int32_t* koff, int64_t n
 
 /* Tile order for the sparse-conv kernels: order[pos] = row, rows sorted (stably) by their neighbour-presence mask
  * mask[j] = OR_k (nbr[k][j] >= 0) << k, so that a 128-row tile touches few distinct offsets and the (tile, offset)
- * pairs without any neighbour can be skipped (what spconv's implicit-GEMM mask sort does).  kvol <= 32, else
- * PV2_EUNSUPPORTED.  Convolution results never depend on the order.
+ * pairs without any neighbour can be skipped (what spconv's implicit-GEMM mask sort does).  For 32 < kvol <= 128 the
+ * key is the mask folded modulo 32; kvol > 128 returns PV2_EUNSUPPORTED.  Convolution results never depend on the order.
  * Optional outputs (may be NULL): nbr_sorted [kvol, n] = the map in tile order, nbr_sorted[k][pos] = nbr[k][order[pos]]
  * (what the conv kernels take together with `order`); blk_active [kvol, ceil(n/32)] = 1 iff any of the 32 consecutive
  * tile-order rows of a block has a neighbour at offset k (the weight-gradient kernel skips the other blocks). */
@@ -116,8 +116,8 @@ int pv2_spconv_wgrad(const void* x, const void* dy, const int32_t* nbr, const in
                      const uint8_t* blk_active, float* dw,
                      int64_t n_in, int64_t n_out, int cin, int cout, int kvol,
                      int dtype, void* workspace, size_t workspace_bytes, void* stream);
-/* scratch of the fp32 tensor-core weight-gradient kernel (split-precision copies of x and dy); without it the
- * exact-fp32 SIMT kernel runs */
+/* scratch of the fp32 tensor-core weight-gradient kernel (dy^T in tile order); without it the exact-fp32 SIMT
+ * kernel runs */
 size_t pv2_wgrad_workspace_bytes(int64_t n_in, int64_t n_out, int cin, int cout);
 
 /* ------------------------------------------------------------------------------------------

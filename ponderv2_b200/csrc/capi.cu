@@ -63,8 +63,8 @@ int pv2_spconv_wgrad(const void* x, const void* dy, const int32_t* nbr, const in
   // tensor-core wgrad pays off once the gathered rows are wide (measured on B200, 100 k voxels, K = 27:
   // 96->96 1.6 vs 2.4 ms, 256->256 6.4 vs 10.1 ms, but 32->32 1.1 vs 0.6 ms): narrow layers stay on the SIMT kernel
   static int min_cin = -1;
-  if (min_cin < 0) { const char* e = getenv("PV2_WGRAD_UMMA_MIN_CIN"); min_cin = e ? atoi(e) : 32; }
-  if (!force_simt() && dtype == PV2_F32 && kvol <= 32 && cin >= min_cin) {
+  if (min_cin < 0) { const char* e = getenv("PV2_WGRAD_UMMA_MIN_CIN"); min_cin = e ? atoi(e) : 8; }
+  if (!force_simt() && dtype == PV2_F32 && kvol <= 128 && cin >= min_cin) {
     int rc = pv2_wgrad_umma((const float*)x, cin, 0, (const float*)dy, cout, 0, nbr, row_order, blk_active, dw, n_in, n_out,
                             cin, cout, kvol, workspace, workspace_bytes, stream);
     if (rc != PV2_EUNSUPPORTED && rc != PV2_EWORKSPACE) return rc;

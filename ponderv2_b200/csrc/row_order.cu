@@ -5,7 +5,7 @@
 // scene) although a surface voxel has ~9 neighbours; grouping rows with equal masks makes the tiles homogeneous (9.6 of
 // 27), which cuts gathered bytes, weight traffic and MMA work by the same factor.  spconv does the same for its
 // implicit-GEMM kernels (mask sort of the indice pairs); results do not depend on the order.
-//   mask[j] = OR_k (nbr[k][j] >= 0) << k          (kvol <= 32)
+//   mask[j] = OR_k (nbr[k][j] >= 0) << (k mod 32)  (exact for kvol <= 32; a folded signature up to kvol = 128)
 //   order   = stable radix sort of rows by mask   (cub::DeviceRadixSort over kvol bits; deterministic)
 #include "pv2_common.cuh"
 #include <cub/device/device_radix_sort.cuh>
@@ -18,7 +18,8 @@ __global__ void row_mask_kernel(const int32_t* __restrict__ nbr, int64_t n, int 
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (; j < n; j += stride) {
     uint32_t m = 0;
-    for (int k = 0; k < kvol; ++k) m |= (uint32_t)(__ldg(&nbr[(int64_t)k * n + j]) >= 0) << k;
+    // K > 32 (the 5x5x5 stem): offsets are folded modulo 32 — a grouping signature, no longer the exact mask
+    for (int k = 0; k < kvol; ++k) m |= (uint32_t)(__ldg(&nbr[(int64_t)k * n + j]) >= 0) << (k & 31);
     mask[j] = m;
     iota[j] = (int32_t)j;
   }
@@ -59,7 +60,8 @@ size_t pv2_rulebook_row_order_workspace_bytes(int64_t n) {
 int pv2_rulebook_row_order(const int32_t* nbr, int64_t n, int kvol, int32_t* order, int32_t* nbr_sorted,
                            uint8_t* blk_active, void* workspace, size_t workspace_bytes, void* stream_) {
   PV2_CHECK_ARG(n >= 0 && kvol >= 1);
-  if (kvol > 32) return PV2_EUNSUPPORTED;
+  if (kvol > 128) return PV2_EUNSUPPORTED;
+  const int key_bits = kvol < 32 ? kvol : 32;
   if (n == 0) return 0;
   PV2_CHECK_ARG(nbr && order && workspace && n < (int64_t)1 << 31);
   if (workspace_bytes < pv2_rulebook_row_order_workspace_bytes(n)) return PV2_EWORKSPACE;
@@ -71,11 +73,11 @@ int pv2_rulebook_row_order(const int32_t* nbr, int64_t n, int kvol, int32_t* ord
   int32_t* iota = (int32_t*)(ws + 2 * a);
   void* temp = ws + 3 * a;
   size_t temp_have = workspace_bytes - 3 * a, temp_need = 0;
-  cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, temp_need, mask_in, mask_out, iota, order, (int)n, 0, kvol, stream);
+  cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, temp_need, mask_in, mask_out, iota, order, (int)n, 0, key_bits, stream);
   if (e != cudaSuccess) return (int)e;
   if (temp_need > temp_have) return PV2_EWORKSPACE;
   row_mask_kernel<<<pv2_grid_for(n, 256), 256, 0, stream>>>(nbr, n, kvol, mask_in, iota);
-  e = cub::DeviceRadixSort::SortPairs(temp, temp_need, mask_in, mask_out, iota, order, (int)n, 0, kvol, stream);
+  e = cub::DeviceRadixSort::SortPairs(temp, temp_need, mask_in, mask_out, iota, order, (int)n, 0, key_bits, stream);
   if (e != cudaSuccess) return (int)e;
   int launches = 2;
   if (nbr_sorted != nullptr || blk_active != nullptr) {

@@ -5,8 +5,8 @@
 // This is a GEMM whose contraction runs over the voxel rows j.  tcgen05's TF32 path takes K-major operands only
 // (measured: setting the MN-major bits of the instruction descriptor with kind::tf32 yields an all-zero accumulator),
 // so both operands are brought into K-major form, i.e. "channel x 32 consecutive rows" tiles:
-//   * A = dY^T: a small transposing split kernel writes dY once as [2 (hi|lo)][Cout][N] and the tile rows are then
-//     plain 128-byte runs copied with cp.async;
+//   * A = dY^T: a small transposing kernel writes dY once as [Cout][N] (rows in tile order) and the tile rows are then
+//     plain 128-byte runs copied RAW with cp.async and split in place into TF32 hi / lo halves once they have landed;
 //   * B = X[nbr[k][j]]^T: gathered rows cannot be pre-transposed (a different permutation per offset k), so each lane
 //     owns one row j, reads its channels with 128-bit loads, splits them into TF32 hi/lo and writes them as a column of
 //     the swizzled tile — lanes of a warp hit 32 different banks, so the transposing stores are conflict-free.
@@ -29,13 +29,14 @@ constexpr int kThreads = 160;
 struct WGParams {
   const float* x;      // [n_in] rows of cin floats, row stride x_row, optional additive second half at +x_lo
   int64_t x_row, x_lo;
-  const float* dyt;    // transposed split dy: [2][cout][np]  (hi plane, lo plane)
+  const float* dyt;    // dy^T in tile order: [cout][np] raw fp32 (split into TF32 halves on chip)
   int64_t np;          // padded row count (multiple of 32) = row length of dyt
   const int32_t* nbr;  // [kvol][n_out] in tile order (nbr[k][pos] feeds output row order[pos]) or nullptr (identity)
   const int32_t* order;  // optional [n_out]: position -> row (mask-sorted, pv2_rulebook_row_order); dyt is in this order
   const uint8_t* blk_active;  // optional [kvol][ceil(n_out/32)]: 1 iff the 32-row block has a pair at offset k
   int max_iters;       // rows_per_chunk / 32 (capacity of the active-stage list)
-  float* dw;           // [cout][kvol][cin]
+  float* dw;           // [cout][kvol][dw_row] (already offset to this launch's first input channel)
+  int64_t dw_row;      // full Cin of the weight tensor (cin below may be a <= 256-wide slice of it)
   int64_t n_out;
   int cin, cout, kvol;
   int n_pad;           // cin rounded up to 16
@@ -182,8 +183,7 @@ __global__ void __launch_bounds__(kThreads) umma_wgrad_kernel(const WGParams p) 
           const bool ok = (co0 + c) < p.cout;
           const float* g = ok ? p.dyt + ((int64_t)(co0 + c) * p.np + j0 + piece * 4) : p.dyt;
           const uint32_t dst = smem_u32(a_hi) + a_off + i * 2048;
-          cp_async_16(dst, g, ok ? 16u : 0u);
-          cp_async_16(dst + kABytes, ok ? g + (int64_t)p.cout * p.np : p.dyt, ok ? 16u : 0u);
+          cp_async_16(dst, g, ok ? 16u : 0u);   // raw fp32 into the hi tile; split in place once it has landed
         }
         // B: lane = row j; transposing stores (bank = f(lane) only -> conflict-free)
 #pragma unroll
@@ -193,8 +193,9 @@ __global__ void __launch_bounds__(kThreads) umma_wgrad_kernel(const WGParams p) 
             const float vv[4] = {xcur[q].x, xcur[q].y, xcur[q].z, xcur[q].w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              float h, l;
-              split_tf32_dev(vv[e], h, l);
+              // hi = top 19 bits (exactly a TF32 number), lo = v - hi (exact)
+              const float h = __uint_as_float(__float_as_uint(vv[e]) & 0xffffe000u);
+              const float l = vv[e] - h;
               const uint32_t off = sw128_offset(u * 4 + e, jc) + col;
               *reinterpret_cast<float*>(b_hi + off) = h;
               *reinterpret_cast<float*>(b_hi + b_bytes + off) = l;
@@ -211,6 +212,22 @@ __global__ void __launch_bounds__(kThreads) umma_wgrad_kernel(const WGParams p) 
           case 2: cp_async_wait<2>(); break;
           default: cp_async_wait<3>(); break;
         }
+        {
+          // this thread's eight A pieces of stage (it - lag) have landed: split them in place
+          const uint32_t a2 = smem_u32(smem + (size_t)((it - lag) % p.stages) * stage_bytes) + a_off;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float4 v;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a2 + i * 2048) : "memory");
+            float4 h, l;
+            h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = v.x - h.x;
+            h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
+            h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - h.z;
+            h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a2 + i * 2048), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a2 + i * 2048 + kABytes), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
+          }
+        }
         fence_proxy_async_smem();
         mbar_arrive(smem_u32(&full_bar[(it - lag) % p.stages]));
       }
@@ -225,7 +242,7 @@ __global__ void __launch_bounds__(kThreads) umma_wgrad_kernel(const WGParams p) 
         tmem_ld_x16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)col0, v);
         tmem_ld_wait();
         if (co >= p.cout) continue;
-        float* dst = p.dw + ((int64_t)co * p.kvol + k) * p.cin + col0;
+        float* dst = p.dw + ((int64_t)co * p.kvol + k) * p.dw_row + col0;
         if (col0 + 16 <= p.cin) {
 #pragma unroll
           for (int q = 0; q < 4; ++q)
@@ -271,7 +288,7 @@ __global__ void __launch_bounds__(kThreads) umma_wgrad_kernel(const WGParams p) 
   }
 }
 
-// dy [rows][cols] (row stride in_row, optional additive half at +in_lo) -> out[2][cols][np] = TF32 hi / lo planes of dy^T,
+// dy [rows][cols] (row stride in_row, optional additive half at +in_lo) -> out[cols][np] = dy^T (rows taken in `order`),
 // zero-padded for rows in [rows, np).  32 x 32 tiles through shared memory: coalesced on both sides.
 __global__ void __launch_bounds__(256) transpose_split_kernel(const float* __restrict__ in, int64_t in_row, int64_t in_lo,
                                                              const int32_t* __restrict__ order, float* __restrict__ out,
@@ -298,10 +315,7 @@ __global__ void __launch_bounds__(256) transpose_split_kernel(const float* __res
     const int c = c0 + ty + 8 * i;
     const int64_t r = r0 + tx;
     if (c < cols && r < np) {
-      float h, l;
-      split_tf32_dev(tile[tx][ty + 8 * i], h, l);
-      out[(int64_t)c * np + r] = h;
-      out[((int64_t)cols + c) * np + r] = l;
+      out[(int64_t)c * np + r] = tile[tx][ty + 8 * i];
     }
   }
 }
@@ -350,7 +364,7 @@ extern "C" {
 size_t pv2_wgrad_workspace_bytes(int64_t n_in, int64_t n_out, int cin, int cout) {
   if (n_in < 0 || n_out < 0) return 0;
   const int64_t np = (n_out + 31) / 32 * 32;
-  return ((size_t)np * cout * 8 + 255) / 256 * 256;
+  return ((size_t)np * cout * 4 + 255) / 256 * 256;
 }
 
 // fp32 only.  x [n_in][cin] / dy [n_out][cout] may carry a row stride and an additive second half (+lo offset), so the
@@ -363,7 +377,7 @@ int pv2_wgrad_umma(const float* x, int64_t x_row, int64_t x_lo, const float* dy,
   PV2_CHECK_ARG(n_in >= 0 && n_out >= 0 && cin > 0 && cout > 0 && kvol > 0);
   if (n_out == 0 || n_in == 0) return 0;
   PV2_CHECK_ARG(x && dy && dw);
-  if ((cin % 4) || cin > 256 || (x_row % 4) || (x_lo % 4) || ((uintptr_t)x & 15)) return PV2_EUNSUPPORTED;
+  if ((cin % 4) || (cin > 256 && (cin % 16)) || (x_row % 4) || (x_lo % 4) || ((uintptr_t)x & 15)) return PV2_EUNSUPPORTED;
   if (nbr == nullptr && (kvol != 1 || n_in != n_out)) return PV2_EINVAL;
   if (workspace == nullptr || workspace_bytes < pv2_wgrad_workspace_bytes(n_in, n_out, cin, cout) ||
       ((uintptr_t)workspace & 15))
@@ -378,8 +392,19 @@ int pv2_wgrad_umma(const float* x, int64_t x_row, int64_t x_lo, const float* dy,
   p.x = x; p.x_row = x_row; p.x_lo = x_lo; p.dyt = dyt; p.np = np; p.nbr = nbr; p.order = (nbr != nullptr) ? order : nullptr;
   p.blk_active = (nbr != nullptr) ? blk_active : nullptr;
   p.dw = dw;
-  p.n_out = n_out; p.cin = cin; p.cout = cout; p.kvol = kvol;
-  return launch_wgrad(p, stream);
+  p.n_out = n_out; p.cout = cout; p.kvol = kvol; p.dw_row = cin;
+  // the accumulator holds N = Cin <= 256 columns: wider inputs (dec3's 384-channel concat) run as balanced slices
+  const int nsl = (cin + 255) / 256;
+  const int per = ((cin + nsl - 1) / nsl + 15) / 16 * 16;
+  for (int ci0 = 0; ci0 < cin; ci0 += per) {
+    WGParams q = p;
+    q.cin = (cin - ci0 < per) ? cin - ci0 : per;
+    q.x = x + ci0;
+    q.dw = dw + ci0;
+    const int rc = launch_wgrad(q, stream);
+    if (rc != 0) return rc;
+  }
+  return 0;
 }
 
 }  // extern "C"

@@ -53,7 +53,7 @@ def build_tile_map(nbr: torch.Tensor) -> TileMap:
     the map permuted into that order, and the per-32-row-block activity bytes of the weight-gradient kernel.
     Maps the tile-skipping kernels do not use (K > 32, K = 1, empty) stay in natural order."""
     kvol, n = nbr.shape
-    if not USE_ROW_ORDER or kvol > 32 or kvol < 2 or n == 0:
+    if not USE_ROW_ORDER or kvol > 128 or kvol < 2 or n == 0:
         return TileMap(nbr)
     lib = _lib.load()
     dev = nbr.device
@@ -209,6 +209,14 @@ class _SparseConvFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, map_fwd: TileMap, map_bwd: TileMap, n_out: int, flip: bool):
         cout, cin = weight.shape[0], weight.shape[-1]
+        ctx.cin_orig = cin
+        if cin % 8 != 0:
+            # ragged stems (6 colour+normal / 4 xyz+strength channels): zero-pad to 8 so that the rows are whole 16-byte
+            # pieces for the tensor-core kernels; the padded weight columns never see a gradient
+            pad = 8 - cin % 8
+            x = torch.nn.functional.pad(x, (0, pad))
+            weight = torch.nn.functional.pad(weight, (0, pad))
+            cin += pad
         compute_dtype = x.dtype
         if torch.is_autocast_enabled():
             compute_dtype = torch.get_autocast_dtype("cuda")
@@ -222,7 +230,7 @@ class _SparseConvFunction(torch.autograd.Function):
         ctx.map_fwd, ctx.map_bwd = map_fwd, map_bwd
         ctx.flip = flip
         ctx.has_bias = bias is not None
-        ctx.weight_shape = weight.shape
+        ctx.weight_shape = weight.shape   # padded shape when cin was ragged; sliced back in backward
         ctx.weight_dtype = weight.dtype
         ctx.x_dtype = x.dtype
         return y
@@ -235,9 +243,9 @@ class _SparseConvFunction(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             wt = w3.flip(1) if ctx.flip else w3
             wt = wt.permute(2, 1, 0).contiguous()  # [Cin, K, Cout]
-            dx = _gather_gemm(dy, wt, None, ctx.map_bwd, xc.shape[0]).to(ctx.x_dtype)
+            dx = _gather_gemm(dy, wt, None, ctx.map_bwd, xc.shape[0]).to(ctx.x_dtype)[:, :ctx.cin_orig]
         if ctx.needs_input_grad[1]:
-            dw = _wgrad(xc, dy, ctx.map_fwd, w3.shape[1]).reshape(ctx.weight_shape).to(ctx.weight_dtype)
+            dw = _wgrad(xc, dy, ctx.map_fwd, w3.shape[1]).reshape(ctx.weight_shape).to(ctx.weight_dtype)[..., :ctx.cin_orig]
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = dy.float().sum(0)
         return dx, dw, db, None, None, None, None

@@ -206,6 +206,7 @@ def _conv_case(kind, cin, cout, dtype, seed, n=1500):
 
 @pytest.mark.parametrize("kind,cin,cout", [
     ("subm3", 32, 32), ("subm3", 64, 96), ("subm3", 192, 128), ("subm5", 6, 32), ("subm1", 128, 96),
+    ("subm3", 384, 256),   # dec3: the 384-wide data gradient / weight gradient run as two column slices
     ("subm3", 7, 13), ("down", 32, 64), ("updown", 64, 96), ("subm5", 4, 32),
 ])
 def test_sparse_conv_fp32(cuda_lib, kind, cin, cout):
