@@ -86,11 +86,15 @@ __global__ void __launch_bounds__(256) field_sample_fwd_kernel(const float* __re
     }
     const int ch = sub * 4;
     if (ch < ca) {
-      float4 h, l;
-      split_tf32(acc.x, h.x, l.x); split_tf32(acc.y, h.y, l.y); split_tf32(acc.z, h.z, l.z); split_tf32(acc.w, h.w, l.w);
       float* dst = out_a + pt * a_row + ch;
-      *reinterpret_cast<float4*>(dst) = h;
-      *reinterpret_cast<float4*>(dst + a_lo) = l;
+      if (a_lo == 0) {   // plain fp32 (the tensor-core layers split on chip)
+        *reinterpret_cast<float4*>(dst) = acc;
+      } else {
+        float4 h, l;
+        split_tf32(acc.x, h.x, l.x); split_tf32(acc.y, h.y, l.y); split_tf32(acc.z, h.z, l.z); split_tf32(acc.w, h.w, l.w);
+        *reinterpret_cast<float4*>(dst) = h;
+        *reinterpret_cast<float4*>(dst + a_lo) = l;
+      }
     } else {
       *reinterpret_cast<float4*>(out_b + pt * b_row + (ch - ca)) = acc;
     }
@@ -166,8 +170,8 @@ __global__ void __launch_bounds__(256) field_post_fwd_kernel(const float* __rest
 // ---------------------------------------------------------------------------------------------------------------
 // Backward of field_post.  Per point:
 //   zbar = g_rgb * rgb (1 - rgb);  inbar = Mr^T zbar;  gbar = g_grad + inbar[0:3]          (total gradient on d sdf/d p)
-//   d f_r = inbar[3:67]  -> dF[:, cs:2cs];  d geo = inbar[67:131], d sdf = g_sdf  -> doutbar [P, 68] (split-precision)
-//   ubar  = sum_i (dw_i . gbar) V_i[0:cs]  -> split-precision [P,2,64]  (second-order term: d grad / d u)
+//   d f_r = inbar[3:67]  -> dF[:, cs:2cs];  d geo = inbar[67:131], d sdf = g_sdf  -> doutbar [P, 68]
+//   ubar  = sum_i (dw_i . gbar) V_i[0:cs]  -> [P,64]  (second-order term: d grad / d u)
 //   dMr  += zbar (x) in,  dcr += zbar     (block partial sums, then atomics)
 __global__ void __launch_bounds__(256) field_post_bwd_kernel(
     const float* __restrict__ vol, const float* __restrict__ pts, const float* __restrict__ dirs, int samples_per_ray,
@@ -219,22 +223,14 @@ __global__ void __launch_bounds__(256) field_post_bwd_kernel(
       dge[i] = Ms[cg] * zb[0] + Ms[134 + cg] * zb[1] + Ms[268 + cg] * zb[2];
     }
     *reinterpret_cast<float4*>(dF + pt * dF_row + 64 + sub * 4) = make_float4(dfr[0], dfr[1], dfr[2], dfr[3]);
-    // doutbar row (68 wide, split-precision [P][2][68]): col 0 = d sdf, cols 1..64 = d geo, cols 65..67 = 0
+    // doutbar row (68 wide, plain fp32): col 0 = d sdf, cols 1..64 = d geo, cols 65..67 = 0
     {
-      float* row = doutbar + pt * 136;
+      float* row = doutbar + pt * 68;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float h, l;
-        split_tf32(dge[i], h, l);
-        row[1 + sub * 4 + i] = h;
-        row[68 + 1 + sub * 4 + i] = l;
-      }
+      for (int i = 0; i < 4; ++i) row[1 + sub * 4 + i] = dge[i];
       if (sub == 0) {
-        float h, l;
-        split_tf32(__ldg(g_sdf + pt), h, l);
-        row[0] = h; row[68] = l;
+        row[0] = __ldg(g_sdf + pt);
         row[65] = row[66] = row[67] = 0.f;
-        row[68 + 65] = row[68 + 66] = row[68 + 67] = 0.f;
         gbar_out[pt * 3 + 0] = gb[0]; gbar_out[pt * 3 + 1] = gb[1]; gbar_out[pt * 3 + 2] = gb[2];
       }
     }
@@ -247,13 +243,7 @@ __global__ void __launch_bounds__(256) field_post_bwd_kernel(
       const float4 v = __ldg(reinterpret_cast<const float4*>(vol + c.off[s]) + sub);
       ub = f4_fma(coef, v, ub);
     }
-    {
-      float4 h, l;
-      split_tf32(ub.x, h.x, l.x); split_tf32(ub.y, h.y, l.y); split_tf32(ub.z, h.z, l.z); split_tf32(ub.w, h.w, l.w);
-      float* dst = ubar + pt * 128 + sub * 4;
-      *reinterpret_cast<float4*>(dst) = h;
-      *reinterpret_cast<float4*>(dst + 64) = l;
-    }
+    *reinterpret_cast<float4*>(ubar + pt * 64 + sub * 4) = ub;
     // dMr partial sums
     const float4 fr = __ldg(reinterpret_cast<const float4*>(f_r + pt * 64) + sub);
     const float* gp = out_geo + pt * geo_row + sub * 4;

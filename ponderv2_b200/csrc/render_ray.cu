@@ -485,7 +485,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) ray_loss_kernel(const Los
       const float sdf = p.sdf[e], z = p.z[e];
       const bool front = valid && (z < gt - p.trunc);
       const bool back = valid && (z > gt + p.trunc);
-      const bool sm = valid && !front && !back;
+      const bool sm = valid && !(front || back);   // written this way on purpose: nvcc 12.9 miscompiles `valid && !front && !back` (drops the `back` test)
       const float gx = p.grad[e * 3], gy = p.grad[e * 3 + 1], gz = p.grad[e * 3 + 2];
       const float nrm = sqrtf(gx * gx + gy * gy + gz * gz);
       const float fs = p.trunc - sdf;

@@ -53,8 +53,15 @@ extern "C" {
 
 size_t pv2_rulebook_row_order_workspace_bytes(int64_t n) {
   if (n < 0) return 0;
-  // mask in/out + iota + cub temporaries (histograms + per-tile look-back state)
-  return 3 * align256((size_t)n * 4) + align256((size_t)n * 2 + (4u << 20));
+  // mask in/out + iota + cub temporaries.  cub reports its need exactly when a device is present; without one (symbol
+  // checks on a CPU-only box) a generous bound is returned.
+  size_t temp = 0;
+  uint32_t* k = nullptr; int32_t* v = nullptr;
+  if (cub::DeviceRadixSort::SortPairs(nullptr, temp, k, k, v, v, (int)n, 0, 32, (cudaStream_t)0) != cudaSuccess) {
+    (void)cudaGetLastError();
+    temp = (size_t)n * 16 + (16u << 20);
+  }
+  return 3 * align256((size_t)n * 4) + align256(temp + 256);
 }
 
 int pv2_rulebook_row_order(const int32_t* nbr, int64_t n, int kvol, int32_t* order, int32_t* nbr_sorted,

@@ -8,11 +8,13 @@
 // order, so the 128 indices of an offset are one coalesced line): a (tile, offset) pair in which
 // no row has a neighbour is skipped by every role, so mask-sorted tiles run ~K_present instead of K offsets.
 // The contraction runs over the concatenated axis (kernel offset k, input channel ci) in chunks of 128 bytes per row:
-//   * warps 0-7 are producers: 256 threads issue 16-byte cp.async (LDGSTS, zero-fill for missing neighbours) straight
-//     into the 128B-swizzled K-major layout tcgen05.mma consumes, several chunks in flight per thread.  fp32 rows are
-//     gathered RAW (4 B per element through L2, not a pre-split 8 B copy) and split in place in shared memory into
-//     two TF32 halves by the thread that copied them; 3xTF32 (hi*hi + lo*hi + hi*lo, ~2^-20 relative error) gives
-//     fp32-grade results from the tensor pipe;
+//   * warps 0-7 are producers.  bf16: all 256 threads issue 16-byte cp.async (LDGSTS, zero-fill for missing neighbours)
+//     straight into the 128B-swizzled K-major layout tcgen05.mma consumes.  fp32: the rows are gathered RAW (4 B per
+//     element through L2, not a pre-split 8 B copy), split in registers into two TF32 halves and stored with 128-bit
+//     st.shared; two groups of four warps alternate chunks so that one group's loads are in flight while the other
+//     group splits/stores (measured on B200: 1.5x faster than cp.async + in-place split, which doubles the shared-memory
+//     traffic of a kernel whose 3xTF32 MMAs already read 84 KB of operands per chunk).  3xTF32 (hi*hi + lo*hi + hi*lo,
+//     ~2^-20 relative error) gives fp32-grade results from the tensor pipe;
 //   * warp 8 issues tcgen05.mma (M = 128, N = Cout padded to 16) into a TMEM accumulator, releasing smem stages with
 //     tcgen05.commit -> mbarrier;
 //   * warps 0-7 then drain TMEM (tcgen05.ld 32x32b), add the bias and write every output row exactly once (no atomics).
@@ -86,17 +88,9 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, const float4& v) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-__device__ __forceinline__ float4 ld_shared_v4(uint32_t addr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
-  return v;
-}
-
-// 16 raw fp32 bytes at `addr` (hi tile) -> hi = top 19 bits (a TF32 number, whatever rounding the tensor core applies to
-// its 32-bit containers), lo = v - hi (exact in fp32; the tensor core keeps its leading 11 bits) at `addr + lo_delta`.
-// hi*hi + lo*hi + hi*lo then carries ~2^-20 relative error per product.
-__device__ __forceinline__ void split_in_place(uint32_t addr, uint32_t lo_delta) {
-  const float4 v = ld_shared_v4(addr);
+// split a float4 and store the halves at `addr` (hi tile) and `addr + lo_delta` (lo tile): hi = top 19 bits (exactly a
+// TF32 number), lo = v - hi (exact in fp32; the tensor core keeps its leading bits)
+__device__ __forceinline__ void split_store(uint32_t addr, uint32_t lo_delta, const float4& v) {
   float4 h, l;
   h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = v.x - h.x;
   h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
@@ -144,7 +138,7 @@ __global__ void __launch_bounds__(kThreads) umma_gather_gemm_kernel(const GGPara
   }
   if (tid == 0) {
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(smem_u32(&full_bar[s]), kProducerThreads);
+      mbar_init(smem_u32(&full_bar[s]), kSplit ? kProducerThreads / 2 : kProducerThreads);
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
     mbar_init(smem_u32(tmem_full_bar), 1);
@@ -241,14 +235,78 @@ __global__ void __launch_bounds__(kThreads) umma_gather_gemm_kernel(const GGPara
     using E = typename T::Elt;
     const E* x = reinterpret_cast<const E*>(p.x);
     const E* w = reinterpret_cast<const E*>(p.w);
-    {
-      // One producer scheme for both storage types: 16-byte cp.async (LDGSTS, zero-fill for missing neighbours and
-      // padding) straight into the swizzled K-major tiles, `lag` chunks in flight per thread.  fp32 rows arrive RAW in
-      // the hi tile; once a thread's own copies of a chunk have landed it splits them in place (hi = the top 19 bits,
-      // exactly representable in TF32; lo = v - hi, exact) into the hi and lo tiles.  No registers are held across the
-      // memory latency and nothing is pre-split in global memory.
+    if constexpr (kSplit) {
+      const int grp = warp >> 2;       // chunks it = grp, grp + 2, ...
+      const int tg = tid & 127;
+      const int piece = tg & 7;
+      const int rbase = tg >> 3;       // 0..15; rows rbase + 16 i keep r & 7, so the swizzled offset advances 2048 B per i
+      const uint32_t tile_off = sw128_offset(rbase, piece);
+      const int nb = p.n_pad >> 4;     // weight rows per thread (1..16)
+      const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int it = grp; it < n_active; it += 2) {
+        const int c = chunk_at(it);
+        const int s = it % p.stages;
+        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+        const int e0 = c * T::kEPR + piece * T::kEPP;
+        const bool kvalid = e0 < ktot;
+        const int k = kvalid ? e0 / p.cin : 0;
+        const int ci = kvalid ? e0 - k * p.cin : 0;
+        const int32_t* idx_k = idx_s + k * kTileM;
+        // every global load of the chunk is issued before anything waits
+        float4 va[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int32_t src = kvalid ? idx_k[rbase + 16 * i] : -1;
+          va[i] = zero4;
+          if (src >= 0) {
+            const float* g = x + ((int64_t)src * p.x_row + ci);
+            va[i] = __ldg(reinterpret_cast<const float4*>(g));
+          }
+        }
+        if constexpr (kPre) {   // split-precision input: add the lo halves (second batch of loads, then the adds)
+          float4 vl[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int32_t src = kvalid ? idx_k[rbase + 16 * i] : -1;
+            vl[i] = zero4;
+            if (src >= 0) vl[i] = __ldg(reinterpret_cast<const float4*>(x + ((int64_t)src * p.x_row + ci) + p.x_lo_off));
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { va[i].x += vl[i].x; va[i].y += vl[i].y; va[i].z += vl[i].z; va[i].w += vl[i].w; }
+        }
+        const float* wk = w + ((int64_t)k * p.w_sk + ci);
+        float4 vb[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int n = rbase + 16 * i;
+          vb[i] = zero4;
+          if (kvalid && i < nb && n < p.cout) vb[i] = __ldg(reinterpret_cast<const float4*>(wk + (int64_t)n * p.w_sco));
+        }
+        mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+        const uint32_t a_dst = smem_u32(stage_base + (size_t)s * stage_bytes) + tile_off;
+        const uint32_t b_dst = a_dst + 2 * kABytes;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) split_store(a_dst + i * 2048, kABytes, va[i]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (i < nb) split_store(b_dst + i * 2048, (uint32_t)b_bytes, vb[i]);
+        if (nb > 8) {  // wide layers (Cout > 128): second half of the weight rows
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int n = rbase + 16 * (i + 8);
+            vb[i] = zero4;
+            if (kvalid && i + 8 < nb && n < p.cout) vb[i] = __ldg(reinterpret_cast<const float4*>(wk + (int64_t)n * p.w_sco));
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (i + 8 < nb) split_store(b_dst + (i + 8) * 2048, (uint32_t)b_bytes, vb[i]);
+        }
+        fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core's async-proxy reads
+        mbar_arrive(smem_u32(&full_bar[s]));
+      }
+    } else {
       const int piece = tid & 7;
-      const int rbase = tid >> 3;      // 0..31; rows rbase + 32 i keep r & 7, so the swizzled offset advances 4096 B per i
+      const int rbase = tid >> 3;      // 0..31; rows rbase + 32 i -> +4096 B per i
       const uint32_t tile_off = sw128_offset(rbase, piece);
       const int lag = p.stages - 1;
       for (int it = 0; it < n_active + lag; ++it) {
@@ -257,6 +315,7 @@ __global__ void __launch_bounds__(kThreads) umma_gather_gemm_kernel(const GGPara
           const int s = it % p.stages;
           const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
           mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+          uint8_t* a_tile = stage_base + (size_t)s * stage_bytes;
           const int e0 = c * T::kEPR + piece * T::kEPP;
           const bool kvalid = e0 < ktot;
           const int k = kvalid ? e0 / p.cin : 0;
@@ -265,15 +324,13 @@ __global__ void __launch_bounds__(kThreads) umma_gather_gemm_kernel(const GGPara
           int32_t src[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) src[i] = kvalid ? idx_k[rbase + 32 * i] : -1;
-          const uint32_t a_dst = smem_u32(stage_base + (size_t)s * stage_bytes) + tile_off;
+          const uint32_t a_dst = smem_u32(a_tile) + tile_off;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const E* g = (src[i] >= 0) ? x + ((int64_t)src[i] * p.x_row + ci) : x;
-            const uint32_t nbytes = src[i] >= 0 ? 16u : 0u;
-            cp_async_16(a_dst + i * 4096, g, nbytes);
-            if constexpr (kPre) cp_async_16(a_dst + i * 4096 + kABytes, g + p.x_lo_off, nbytes);   // stored lo half
+            cp_async_16(a_dst + i * 4096, g, src[i] >= 0 ? 16u : 0u);
           }
-          const uint32_t b_dst = a_dst + kABytes * T::kOperands;
+          const uint32_t b_dst = a_dst + kABytes;
           const E* wk = w + ((int64_t)k * p.w_sk + ci);
           for (int n = rbase, i = 0; n < p.n_pad; n += 32, ++i) {
             const bool ok = kvalid && n < p.cout;
@@ -282,7 +339,7 @@ __global__ void __launch_bounds__(kThreads) umma_gather_gemm_kernel(const GGPara
         }
         cp_async_commit();
         if (it >= lag) {
-          // chunk (it - lag) has landed for this thread
+          // chunk (it - lag) has landed for this thread: make it visible to the async proxy and signal
           switch (lag) {  // wait_group needs an immediate
             case 1: cp_async_wait<1>(); break;
             case 2: cp_async_wait<2>(); break;
@@ -290,18 +347,8 @@ __global__ void __launch_bounds__(kThreads) umma_gather_gemm_kernel(const GGPara
             case 4: cp_async_wait<4>(); break;
             default: cp_async_wait<5>(); break;
           }
-          const int s2 = (it - lag) % p.stages;
-          if constexpr (kSplit) {
-            const uint32_t a2 = smem_u32(stage_base + (size_t)s2 * stage_bytes) + tile_off;
-            if constexpr (!kPre) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) split_in_place(a2 + i * 4096, kABytes);
-            }
-            const uint32_t b2 = a2 + 2 * kABytes;
-            for (int n = rbase, i = 0; n < p.n_pad; n += 32, ++i) split_in_place(b2 + i * 4096, (uint32_t)b_bytes);
-          }
-          fence_proxy_async_smem();   // generic-proxy / cp.async writes -> visible to the tensor core's async-proxy reads
-          mbar_arrive(smem_u32(&full_bar[s2]));
+          fence_proxy_async_smem();
+          mbar_arrive(smem_u32(&full_bar[(it - lag) % p.stages]));
         }
       }
     }

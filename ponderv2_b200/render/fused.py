@@ -61,15 +61,15 @@ def coarse_sdf(vol_cl: torch.Tensor, pts: torch.Tensor, M0, c0, wcat4, c14) -> t
     Z, Y, X, C = _vol_dims(vol_cl)
     P = pts.shape[0]
     dev = pts.device
-    xa = torch.empty((P, 2, 192), dtype=torch.float32, device=dev)  # [a(128) | f_s(64)], split-precision
+    xa = torch.empty((P, 192), dtype=torch.float32, device=dev)  # [a(128) | f_s(64)], plain fp32 (split on chip)
     pts = pts.contiguous()
     with torch.cuda.device(dev):
         _lib.check(lib.pv2_field_sample_fwd(_lib.ptr(vol_cl), _lib.ptr(pts), P, Z, Y, X, C, 64, 64,
-                                            _lib.C.c_void_p(xa.data_ptr() + 128 * 4), 384, 192, None, 0,
+                                            _lib.C.c_void_p(xa.data_ptr() + 128 * 4), 192, 0, None, 0,
                                             _lib.stream_ptr()), "pv2_field_sample_fwd")
-    _linear(xa[:, :, 128:], 384, 192, True, M0, c0, xa, 384, 192, True, 1, None, 0, 0, P, 64, 128)
+    _linear(xa[:, 128:], 192, 0, False, M0, c0, xa, 192, 0, False, 1, None, 0, 0, P, 64, 128)
     out = torch.empty((P, 4), dtype=torch.float32, device=dev)
-    _linear(xa, 384, 192, True, wcat4, c14, out, 4, 0, False, 0, None, 0, 0, P, 192, 4)
+    _linear(xa, 192, 0, False, wcat4, c14, out, 4, 0, False, 0, None, 0, 0, P, 192, 4)
     return out[:, 0]
 
 
@@ -86,8 +86,8 @@ class FusedFieldFunction(torch.autograd.Function):
         dev = pts.device
         pts = pts.contiguous()
         dirs = dirs.contiguous()
-        xa = torch.empty((P, 2, 192), dtype=torch.float32, device=dev)   # [a | f_s] split-precision
-        s_split = torch.empty((P, 2, 128), dtype=torch.float32, device=dev)
+        xa = torch.empty((P, 192), dtype=torch.float32, device=dev)      # [a | f_s] plain fp32
+        s_act = torch.empty((P, 128), dtype=torch.float32, device=dev)   # sigmoid(100 h) = d softplus / d h
         f_r = torch.empty((P, 64), dtype=torch.float32, device=dev)
         out = torch.empty((P, 68), dtype=torch.float32, device=dev)      # [sdf | geo(64) | 0 0 0]
         u = torch.empty((P, 64), dtype=torch.float32, device=dev)
@@ -96,27 +96,27 @@ class FusedFieldFunction(torch.autograd.Function):
         sp = _lib.stream_ptr
         with torch.cuda.device(dev):
             _lib.check(lib.pv2_field_sample_fwd(_lib.ptr(vol_cl), _lib.ptr(pts), P, Z, Y, X, C, 128, 64,
-                                                _lib.C.c_void_p(xa.data_ptr() + 128 * 4), 384, 192, _lib.ptr(f_r), 64,
+                                                _lib.C.c_void_p(xa.data_ptr() + 128 * 4), 192, 0, _lib.ptr(f_r), 64,
                                                 sp()), "pv2_field_sample_fwd")
-        # h = M0 f_s + c0 -> a (into xa[:, :, 0:128]) and s
-        _linear(xa[:, :, 128:], 384, 192, True, M0, c0, xa, 384, 192, True, 1, s_split, 256, 128, P, 64, 128)
+        # h = M0 f_s + c0 -> a (into xa[:, 0:128]) and s
+        _linear(xa[:, 128:], 192, 0, False, M0, c0, xa, 192, 0, False, 1, s_act, 128, 0, P, 64, 128)
         # out = [W1 | M1] [a | f_s] + c1
-        _linear(xa, 384, 192, True, wcat, c1, out, 68, 0, False, 0, None, 0, 0, P, 192, 68)
+        _linear(xa, 192, 0, False, wcat, c1, out, 68, 0, False, 0, None, 0, 0, P, 192, 68)
         # u = (M0 * W1[0])^T s + M1[0]
-        _linear(s_split, 256, 128, True, wp, m10, u, 64, 0, False, 0, None, 0, 0, P, 128, 64)
+        _linear(s_act, 128, 0, False, wp, m10, u, 64, 0, False, 0, None, 0, 0, P, 128, 64)
         Mr_c, cr_c = Mr.contiguous(), cr.contiguous()
         with torch.cuda.device(dev):
             _lib.check(lib.pv2_field_post_fwd(_lib.ptr(vol_cl), _lib.ptr(pts), _lib.ptr(dirs), samples_per_ray,
                                               _lib.ptr(u), _lib.ptr(f_r), _lib.C.c_void_p(out.data_ptr() + 4), 68,
                                               _lib.ptr(Mr_c), _lib.ptr(cr_c), P, Z, Y, X, C, _lib.ptr(grad),
                                               _lib.ptr(rgb), sp()), "pv2_field_post_fwd")
-        ctx.save_for_backward(vol_cl, pts, dirs, xa, s_split, f_r, out, u, grad, rgb, M0, wcat, wp, Mr_c)
+        ctx.save_for_backward(vol_cl, pts, dirs, xa, s_act, f_r, out, u, grad, rgb, M0, wcat, wp, Mr_c)
         ctx.spr = samples_per_ray
         return out[:, 0].contiguous(), grad, rgb
 
     @staticmethod
     def backward(ctx, g_sdf, g_grad, g_rgb):
-        vol_cl, pts, dirs, xa, s_split, f_r, out, u, grad, rgb, M0, wcat, wp, Mr = ctx.saved_tensors
+        vol_cl, pts, dirs, xa, s, f_r, out, u, grad, rgb, M0, wcat, wp, Mr = ctx.saved_tensors
         lib = _lib.load()
         Z, Y, X, C = _vol_dims(vol_cl)
         P = pts.shape[0]
@@ -125,8 +125,8 @@ class FusedFieldFunction(torch.autograd.Function):
         g_sdf, g_grad, g_rgb = z(g_sdf, (P,)), z(g_grad, (P, 3)), z(g_rgb, (P, 3))
         gbar = torch.empty((P, 3), dtype=torch.float32, device=dev)
         dF = torch.empty((P, 128), dtype=torch.float32, device=dev)
-        doutbar = torch.empty((P, 2, 68), dtype=torch.float32, device=dev)
-        ubar = torch.empty((P, 2, 64), dtype=torch.float32, device=dev)
+        doutbar = torch.empty((P, 68), dtype=torch.float32, device=dev)
+        ubar = torch.empty((P, 64), dtype=torch.float32, device=dev)
         dMr = torch.zeros((3, 134), dtype=torch.float32, device=dev)
         dcr = torch.zeros(3, dtype=torch.float32, device=dev)
         sp = _lib.stream_ptr
@@ -136,23 +136,22 @@ class FusedFieldFunction(torch.autograd.Function):
                                               _lib.ptr(Mr), _lib.ptr(g_rgb), _lib.ptr(g_grad), _lib.ptr(g_sdf), P, Z, Y,
                                               X, C, _lib.ptr(gbar), _lib.ptr(dF), 128, _lib.ptr(doutbar), _lib.ptr(ubar),
                                               _lib.ptr(dMr), _lib.ptr(dcr), sp()), "pv2_field_post_bwd")
-        s = s_split[:, 0] + s_split[:, 1]
         # through u = s wp^T + m10
         sbar = torch.empty((P, 128), dtype=torch.float32, device=dev)
-        _linear(ubar, 128, 64, True, wp.t().contiguous(), None, sbar, 128, 0, False, 0, None, 0, 0, P, 64, 128)
-        d_wp = _dense_wgrad(s_split, 256, 128, ubar, 128, 64, P, 128, 64)
-        d_m10 = (ubar[:, 0] + ubar[:, 1]).sum(0)
+        _linear(ubar, 64, 0, False, wp.t().contiguous(), None, sbar, 128, 0, False, 0, None, 0, 0, P, 64, 128)
+        d_wp = _dense_wgrad(s, 128, 0, ubar, 64, 0, P, 128, 64)
+        d_m10 = ubar.sum(0)
         hbar = sbar * (100.0 * s * (1.0 - s))
         # through out = [a | f_s] wcat^T + c1
         xabar = torch.empty((P, 192), dtype=torch.float32, device=dev)
-        _linear(doutbar, 136, 68, True, wcat.t().contiguous(), None, xabar, 192, 0, False, 0, None, 0, 0, P, 68, 192)
-        d_wcat = _dense_wgrad(xa, 384, 192, doutbar, 136, 68, P, 192, 68)
-        d_c1 = (doutbar[:, 0] + doutbar[:, 1]).sum(0)
+        _linear(doutbar, 68, 0, False, wcat.t().contiguous(), None, xabar, 192, 0, False, 0, None, 0, 0, P, 68, 192)
+        d_wcat = _dense_wgrad(xa, 192, 0, doutbar, 68, 0, P, 192, 68)
+        d_c1 = doutbar.sum(0)
         # through a = softplus(h), h = f_s M0^T + c0
         hbar = hbar + xabar[:, :128] * s
         _linear(hbar, 128, 0, False, M0.t().contiguous(), None, dF, 128, 0, False, 0, None, 0, 0, P, 128, 64)
         dF[:, :64] += xabar[:, 128:]
-        d_M0 = _dense_wgrad(xa[:, :, 128:], 384, 192, hbar, 128, 0, P, 64, 128)
+        d_M0 = _dense_wgrad(xa[:, 128:], 192, 0, hbar, 128, 0, P, 64, 128)
         d_c0 = hbar.sum(0)
         dvol = torch.zeros_like(vol_cl)
         with torch.cuda.device(dev):

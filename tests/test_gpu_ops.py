@@ -125,7 +125,8 @@ def test_row_order_is_stable_mask_sort(cuda_lib, case):
         padded = np.full((nbr_np.shape[0], nblk * 32), -1, np.int32)
         padded[:, :nbr_np.shape[1]] = nbr_np[:, want]
         assert np.array_equal(tm.blk_active.cpu().numpy(), (padded.reshape(nbr_np.shape[0], nblk, 32) >= 0).any(2))
-    assert spconv.build_row_order(torch.zeros((125, 10), dtype=torch.int32, device=_dev())) is None  # K > 32: no order
+    assert spconv.build_row_order(torch.zeros((200, 10), dtype=torch.int32, device=_dev())) is None  # K > 128: no order
+    assert spconv.build_row_order(torch.zeros((125, 10), dtype=torch.int32, device=_dev())) is not None  # 5x5x5: folded key
 
 
 def test_make_indices(cuda_lib):

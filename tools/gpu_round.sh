@@ -5,7 +5,7 @@
 set -u
 tag=${1:-r1}; shift || true
 out=gpurun_out; mkdir -p $out
-timeout 900 python -m pytest tests -m gpu -x -q > $out/${tag}_pytest.log 2>&1; echo "pytest exit $?"
+timeout 900 python -m pytest tests -m gpu -q > $out/${tag}_pytest.log 2>&1; echo "pytest exit $?"
 tail -15 $out/${tag}_pytest.log
 if [ "${SKIP_MICRO:-0}" != "1" ]; then
   timeout 600 python tools/spconv_microbench.py --levels --out $out/${tag}_micro_levels.json 2>&1 | tee $out/${tag}_micro_levels.txt
