@@ -24,6 +24,7 @@
 // HBM-side algorithmic bytes per call: N*Cin*b + N*Cout*b + K*Cin*Cout*b + 4*K*N.
 #include "pv2_common.cuh"
 #include "umma.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -499,6 +500,11 @@ int launch(const GGParams& p0, cudaStream_t stream) {
   const int stage_bytes = (kABytes + p.n_pad * 128) * T::kOperands;
   const int fixed = p.kvol * kTileM * 4 + kTileM * 4 + (p.num_chunks * 2 + 8) + (2 * kMaxStages + 1) * 8 + 128 + 1024;
   int stages = (220 * 1024 - fixed) / stage_bytes;
+  // two resident CTAs per SM when at least two stages fit in half of the shared memory: the second CTA's setup,
+  // gathers and epilogue overlap the first one's main loop (the kernel is latency-bound, not bandwidth-bound)
+  static int want_ctas = -1;
+  if (want_ctas < 0) { const char* e = getenv("PV2_GG_CTAS"); want_ctas = e ? atoi(e) : 2; }
+  if (want_ctas >= 2 && (112 * 1024 - fixed) / stage_bytes >= 2) stages = (112 * 1024 - fixed) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return PV2_EUNSUPPORTED;
   p.stages = stages;

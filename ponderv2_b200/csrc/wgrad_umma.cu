@@ -22,7 +22,7 @@ namespace {
 using namespace pv2;
 
 constexpr int kRowsPerStage = 32;   // contraction rows per pipeline stage = one 128-byte K-major line (4 MMA k-steps)
-constexpr int kABytes = 128 * 128;  // 128 output channels x 128 B
+constexpr int kMaxABytes = 128 * 128;  // 128 output channels x 128 B (the A tile holds only the channels that exist)
 constexpr int kMaxStages = 4;
 constexpr int kThreads = 160;
 
@@ -35,6 +35,8 @@ struct WGParams {
   const int32_t* order;  // optional [n_out]: position -> row (mask-sorted, pv2_rulebook_row_order); dyt is in this order
   const uint8_t* blk_active;  // optional [kvol][ceil(n_out/32)]: 1 iff the 32-row block has a pair at offset k
   int max_iters;       // rows_per_chunk / 32 (capacity of the active-stage list)
+  int a_bytes;         // bytes of one A tile half: round8(min(128, cout)) rows x 128 B.  The MMA (M = 128) reads past it
+                       // into the neighbouring tiles; those rows only feed accumulator lanes >= cout, which nobody reads
   float* dw;           // [cout][kvol][dw_row] (already offset to this launch's first input channel)
   int64_t dw_row;      // full Cin of the weight tensor (cin below may be a <= 256-wide slice of it)
   int64_t n_out;
@@ -55,8 +57,10 @@ __device__ __forceinline__ void split_tf32_dev(float v, float& hi, float& lo) {
 
 // kPre: x is split-precision (value = x[..] + x[.. + x_lo]); a template parameter so that the plain path carries no
 // (predicated-off but still scoreboard-waiting) adds between its gather loads.
-template <bool kPre>
-__global__ void __launch_bounds__(kThreads) umma_wgrad_kernel(const WGParams p) {
+// kUnits: float4 units of a gathered row each lane may hold (8: Cin <= 128, small enough register footprint for two
+// resident CTAs per SM; 16: Cin <= 256).
+template <bool kPre, int kUnits>
+__global__ void __launch_bounds__(kThreads, kUnits == 8 ? 2 : 1) umma_wgrad_kernel(const WGParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -68,6 +72,8 @@ __global__ void __launch_bounds__(kThreads) umma_wgrad_kernel(const WGParams p) 
   const int n_iters = (int)((r_end - r_begin + kRowsPerStage - 1) / kRowsPerStage);
 
   const int b_bytes = p.n_pad * 128;
+  const int kABytes = p.a_bytes;
+  const int a_rows = kABytes >> 7;
   const int stage_bytes = 2 * (kABytes + b_bytes);   // [A_hi][A_lo][B_hi][B_lo]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
   uint64_t* full_bar = bars;
@@ -130,7 +136,7 @@ __global__ void __launch_bounds__(kThreads) umma_wgrad_kernel(const WGParams p) 
     const uint32_t a_off = sw128_offset(cbase, piece);
     const int lag = p.stages - 1;
     const int n_units = p.n_pad / 4;
-    constexpr int kMaxUnitsPerWarp = 16;  // n_pad <= 256 -> 64 units / 4 warps
+    constexpr int kMaxUnitsPerWarp = kUnits;  // n_pad <= 256 -> 64 units / 4 warps
     const int upw = n_units / 4;          // n_pad is a multiple of 16 -> n_units is a multiple of 4
     const uint32_t col = (uint32_t)((lane & 3) * 4);
     const int jc = lane >> 2;
@@ -180,6 +186,7 @@ __global__ void __launch_bounds__(kThreads) umma_wgrad_kernel(const WGParams p) 
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int c = cbase + 16 * i;
+          if (c >= a_rows) continue;              // rows the tile does not hold
           const bool ok = (co0 + c) < p.cout;
           const float* g = ok ? p.dyt + ((int64_t)(co0 + c) * p.np + j0 + piece * 4) : p.dyt;
           const uint32_t dst = smem_u32(a_hi) + a_off + i * 2048;
@@ -217,6 +224,7 @@ __global__ void __launch_bounds__(kThreads) umma_wgrad_kernel(const WGParams p) 
           const uint32_t a2 = smem_u32(smem + (size_t)((it - lag) % p.stages) * stage_bytes) + a_off;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
+            if (cbase + 16 * i >= a_rows) continue;
             float4 v;
             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a2 + i * 2048) : "memory");
             float4 h, l;
@@ -324,12 +332,13 @@ int launch_wgrad(WGParams p, cudaStream_t stream) {
   p.n_pad = (p.cin + 15) / 16 * 16;
   p.tmem_cols = 32;
   while ((int)p.tmem_cols < p.n_pad) p.tmem_cols <<= 1;
-  const int stage_bytes = 2 * (kABytes + p.n_pad * 128);
-  int fixed = (2 * kMaxStages + 2) * 8 + 64 + 1024;   // + the active-stage list, added below
-  int stages = (194 * 1024 - fixed) / stage_bytes;
-  if (stages > kMaxStages) stages = kMaxStages;
-  if (stages < 2) return PV2_EUNSUPPORTED;
-  p.stages = stages;
+  {
+    const int rows = p.cout < 128 ? (p.cout + 7) / 8 * 8 : 128;
+    p.a_bytes = rows * 128;
+  }
+  const int stage_bytes = 2 * (p.a_bytes + p.n_pad * 128);
+  // + the active-stage list (added below) + 16 KB the M = 128 MMA may read past a short A tile of the last stage
+  int fixed = (2 * kMaxStages + 2) * 8 + 64 + 1024 + kMaxABytes;
   const int m_tiles = (p.cout + 127) / 128;
   // ~4 CTAs per SM in total, chunks of at least 256 rows
   int64_t chunks = (4LL * PV2_SM_COUNT + (int64_t)p.kvol * m_tiles - 1) / ((int64_t)p.kvol * m_tiles);
@@ -342,18 +351,37 @@ int launch_wgrad(WGParams p, cudaStream_t stream) {
   chunks = (p.n_out + p.rows_per_chunk - 1) / p.rows_per_chunk;
   p.max_iters = (int)(p.rows_per_chunk / kRowsPerStage);
   fixed += 3 * p.max_iters + 16;
+  // two resident CTAs per SM when two stages fit in half of the shared memory (the kernel is latency-bound: a second
+  // CTA's gathers overlap the first one's splits and stores); otherwise one CTA with up to four stages
+  static int want_ctas = -1;
+  if (want_ctas < 0) { const char* e = getenv("PV2_WGRAD_CTAS"); want_ctas = e ? atoi(e) : 2; }
+  int stages = (194 * 1024 - fixed) / stage_bytes;
+  if (want_ctas >= 2 && (112 * 1024 - fixed) / stage_bytes >= 2) stages = (112 * 1024 - fixed) / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) return PV2_EUNSUPPORTED;
+  p.stages = stages;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(umma_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(umma_wgrad_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(umma_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      e = cudaFuncSetAttribute(umma_wgrad_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(umma_wgrad_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(umma_wgrad_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
   const size_t smem = (size_t)stages * stage_bytes + fixed;
   dim3 grid((unsigned)chunks, (unsigned)p.kvol, (unsigned)m_tiles);
-  if (p.x_lo != 0) umma_wgrad_kernel<true><<<grid, kThreads, smem, stream>>>(p);
-  else umma_wgrad_kernel<false><<<grid, kThreads, smem, stream>>>(p);
+  const bool small = p.n_pad <= 128;
+  if (p.x_lo != 0) {
+    if (small) umma_wgrad_kernel<true, 8><<<grid, kThreads, smem, stream>>>(p);
+    else umma_wgrad_kernel<true, 16><<<grid, kThreads, smem, stream>>>(p);
+  } else {
+    if (small) umma_wgrad_kernel<false, 8><<<grid, kThreads, smem, stream>>>(p);
+    else umma_wgrad_kernel<false, 16><<<grid, kThreads, smem, stream>>>(p);
+  }
   PV2_DONE(1);
 }
 

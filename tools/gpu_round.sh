@@ -9,10 +9,25 @@ timeout 900 python -m pytest tests -m gpu -q > $out/${tag}_pytest.log 2>&1; echo
 tail -15 $out/${tag}_pytest.log
 if [ "${SKIP_MICRO:-0}" != "1" ]; then
   timeout 600 python tools/spconv_microbench.py --levels --out $out/${tag}_micro_levels.json 2>&1 | tee $out/${tag}_micro_levels.txt
+  if [ "${MICRO_AB:-0}" = "1" ]; then
+    PV2_GG_CTAS=1 PV2_WGRAD_CTAS=1 timeout 600 python tools/spconv_microbench.py --levels 2>&1 | tee $out/${tag}_micro_levels_1cta.txt
+  fi
   if [ "${MICRO_NOORDER:-0}" = "1" ]; then
     PV2_ROW_ORDER=0 timeout 600 python tools/spconv_microbench.py --levels 2>&1 | tee $out/${tag}_micro_levels_noorder.txt
   fi
   timeout 600 python tools/spconv_microbench.py --sizes 100000,1000000 --out $out/${tag}_micro_c5.json 2>&1 | tee $out/${tag}_micro_c5.txt
+fi
+if [ "${NCU_MICRO:-0}" = "1" ]; then
+  # one warmed-up launch of each conv kernel at the C2 level-0 decoder shape (100 k voxels, 96 -> 96), full metric set +
+  # per-instruction stall samples (SASS)
+  for kn in umma_gather_gemm umma_wgrad; do
+    timeout 600 ncu --set full --clock-control none -k regex:$kn -s 6 -c 1 -f -o $out/${tag}_micro_$kn \
+        python tools/spconv_microbench.py --sizes 100000 --chans 96 > $out/${tag}_ncu_micro_$kn.log 2>&1
+    echo "ncu micro $kn exit $?"
+    ncu -i $out/${tag}_micro_$kn.ncu-rep --page details --csv > $out/${tag}_micro_${kn}_details.csv 2>/dev/null
+    ncu -i $out/${tag}_micro_$kn.ncu-rep --page raw --csv > $out/${tag}_micro_${kn}_raw.csv 2>/dev/null
+    ncu -i $out/${tag}_micro_$kn.ncu-rep --page source --csv --print-source sass > $out/${tag}_micro_${kn}_source.csv 2>/dev/null
+  done
 fi
 timeout 900 python bench.py --steps 10 --warmup 3 > $out/${tag}_bench.json 2> $out/${tag}_bench.log; echo "bench exit $?"
 cat $out/${tag}_bench.json; tail -3 $out/${tag}_bench.log
