@@ -163,7 +163,8 @@ int pv2_trilinear_bwd_bwd(const void* grad_out_input, const void* grad_out_grid,
  *   y[j, 0:cout] = act(x[j, 0:cin] . w^T + bias);  w is [cout, cin] row-major.
  * x: plain [rows, cin] (x_presplit = 0, x_row = cin) or split-precision (hi at x[j*x_row + c], lo at +x_lo_off).
  * y (and y2 when act = 1): row stride y_row; y_split = 1 writes TF32 hi/lo halves (lo at +y_lo_off).
- * act: 0 none; 1 y = softplus(beta=100, threshold=20), y2 = sigmoid(100 v) (the softplus derivative).
+ * act: 0 none; 1 y = softplus(beta=100, threshold=20), y2 = sigmoid(100 v) (the softplus derivative);
+ *      backward epilogues, y2 [rows, y2_row] an INPUT s: 2 y = v*100*s*(1-s); 3 y = y + v*s; 4 y = y + v.
  * ------------------------------------------------------------------------------------------ */
 size_t pv2_linear_workspace_bytes(int64_t rows, int cin, int cout, int x_presplit);
 int pv2_linear(const float* x, int64_t x_row, int64_t x_lo_off, int x_presplit, const float* w, const float* bias,
@@ -191,7 +192,8 @@ int pv2_field_post_bwd(const float* vol, const float* pts, const float* dirs, in
                        const float* out_geo, int64_t geo_row, const float* grad, const float* rgb, const float* Mr,
                        const float* g_rgb, const float* g_grad, const float* g_sdf, int64_t P, int Z, int Y, int X,
                        int C, float* gbar, float* dF, int64_t dF_row, float* doutbar, float* ubar, float* dMr,
-                       float* dcr, void* stream);
+                       float* dcr, float* ubar_sum /*[64] accumulated, optional*/,
+                       float* dout_sum /*[68] accumulated, optional*/, void* stream);
 /* dvol[corner,c] += w dF[p,c] + [c<cs] (dw.gbar) u[p,c]   (u may be NULL) */
 int pv2_field_sample_bwd(const float* pts, const float* dF, int64_t dF_row, const float* u, const float* gbar,
                          int64_t P, int Z, int Y, int X, int C, int cs, float* dvol, void* stream);

@@ -179,12 +179,13 @@ __global__ void __launch_bounds__(256) field_post_bwd_kernel(
     const float* __restrict__ rgb, const float* __restrict__ Mr, const float* __restrict__ g_rgb,
     const float* __restrict__ g_grad, const float* __restrict__ g_sdf, int64_t P, int Z, int Y, int X, int C,
     float* __restrict__ gbar_out, float* __restrict__ dF, int64_t dF_row, float* __restrict__ doutbar,
-    float* __restrict__ ubar, float* __restrict__ dMr, float* __restrict__ dcr) {
+    float* __restrict__ ubar, float* __restrict__ dMr, float* __restrict__ dcr, float* __restrict__ ubar_sum,
+    float* __restrict__ dout_sum) {
   constexpr int LANES = 16;
   __shared__ float Ms[402];
-  __shared__ float acc_s[405];
+  __shared__ float acc_s[405 + 64 + 68];   // dMr (402) | dcr (3) | column sums of ubar (64) | of doutbar (68)
   for (int i = threadIdx.x; i < 402; i += blockDim.x) Ms[i] = Mr[i];
-  for (int i = threadIdx.x; i < 405; i += blockDim.x) acc_s[i] = 0.f;
+  for (int i = threadIdx.x; i < 405 + 64 + 68; i += blockDim.x) acc_s[i] = 0.f;
   __syncthreads();
   const int sub = threadIdx.x % LANES;
   const int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
@@ -193,6 +194,7 @@ __global__ void __launch_bounds__(256) field_post_bwd_kernel(
   // per-lane partial sums of dMr: rows k, columns {f_r 4 ch, geo 4 ch}; lane 0 also carries grad/dir/bias columns
   float am[3][8];
   float a0[3][7];
+  float us[4] = {0.f, 0.f, 0.f, 0.f}, ds[4] = {0.f, 0.f, 0.f, 0.f}, ds0 = 0.f;   // bias gradients: column sums
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
 #pragma unroll
@@ -227,9 +229,10 @@ __global__ void __launch_bounds__(256) field_post_bwd_kernel(
     {
       float* row = doutbar + pt * 68;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) row[1 + sub * 4 + i] = dge[i];
+      for (int i = 0; i < 4; ++i) { row[1 + sub * 4 + i] = dge[i]; ds[i] += dge[i]; }
       if (sub == 0) {
         row[0] = __ldg(g_sdf + pt);
+        ds0 += row[0];
         row[65] = row[66] = row[67] = 0.f;
         gbar_out[pt * 3 + 0] = gb[0]; gbar_out[pt * 3 + 1] = gb[1]; gbar_out[pt * 3 + 2] = gb[2];
       }
@@ -244,6 +247,7 @@ __global__ void __launch_bounds__(256) field_post_bwd_kernel(
       ub = f4_fma(coef, v, ub);
     }
     *reinterpret_cast<float4*>(ubar + pt * 64 + sub * 4) = ub;
+    us[0] += ub.x; us[1] += ub.y; us[2] += ub.z; us[3] += ub.w;
     // dMr partial sums
     const float4 fr = __ldg(reinterpret_cast<const float4*>(f_r + pt * 64) + sub);
     const float* gp = out_geo + pt * geo_row + sub * 4;
@@ -279,10 +283,20 @@ __global__ void __launch_bounds__(256) field_post_bwd_kernel(
       atomicAdd(&acc_s[402 + k], a0[k][6]);
     }
   }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    atomicAdd(&acc_s[405 + sub * 4 + i], us[i]);
+    atomicAdd(&acc_s[405 + 64 + 1 + sub * 4 + i], ds[i]);
+  }
+  if (sub == 0) atomicAdd(&acc_s[405 + 64], ds0);
   __syncthreads();
-  for (int i = threadIdx.x; i < 405; i += blockDim.x) {
+  for (int i = threadIdx.x; i < 405 + 64 + 68; i += blockDim.x) {
     const float v = acc_s[i];
-    if (v != 0.f) atomicAdd(i < 402 ? &dMr[i] : &dcr[i - 402], v);
+    if (v == 0.f) continue;
+    if (i < 402) atomicAdd(&dMr[i], v);
+    else if (i < 405) atomicAdd(&dcr[i - 402], v);
+    else if (i < 405 + 64) { if (ubar_sum != nullptr) atomicAdd(&ubar_sum[i - 405], v); }
+    else if (dout_sum != nullptr) atomicAdd(&dout_sum[i - 405 - 64], v);
   }
 }
 
@@ -357,7 +371,7 @@ int pv2_field_post_bwd(const float* vol, const float* pts, const float* dirs, in
                        const float* out_geo, int64_t geo_row, const float* grad, const float* rgb, const float* Mr,
                        const float* g_rgb, const float* g_grad, const float* g_sdf, int64_t P, int Z, int Y, int X, int C,
                        float* gbar, float* dF, int64_t dF_row, float* doutbar, float* ubar, float* dMr, float* dcr,
-                       void* stream_) {
+                       float* ubar_sum, float* dout_sum, void* stream_) {
   PV2_CHECK_ARG(P >= 0 && vol_ok(Z, Y, X, C) && C >= 64 && samples_per_ray > 0);
   if (P == 0) return 0;
   PV2_CHECK_ARG(vol && pts && dirs && f_r && out_geo && grad && rgb && Mr && g_rgb && g_grad && g_sdf && gbar && dF &&
@@ -365,7 +379,7 @@ int pv2_field_post_bwd(const float* vol, const float* pts, const float* dirs, in
   // bounded grid: every block ends with ~400 atomics for the colour-head weight gradient
   field_post_bwd_kernel<<<pv2_grid_for(P * 16, 256, 2), 256, 0, (cudaStream_t)stream_>>>(
       vol, pts, dirs, samples_per_ray, f_r, out_geo, geo_row, grad, rgb, Mr, g_rgb, g_grad, g_sdf, P, Z, Y, X, C, gbar,
-      dF, dF_row, doutbar, ubar, dMr, dcr);
+      dF, dF_row, doutbar, ubar, dMr, dcr, ubar_sum, dout_sum);
   PV2_DONE(1);
 }
 

@@ -57,6 +57,7 @@ struct GGParams {
   int64_t y_row, y_lo_off;
   int y_split;       // fp32 only: write TF32 hi/lo halves instead of the plain value
   int act;           // 0: none; 1: y = softplus(beta=100, threshold=20)(v), y2 = sigmoid(100 v)   (SDF decoder, decoders.py:24)
+                     // 2..4: backward epilogues reading y2 / the old y (see the epilogue)
   void* y2;
   int64_t y2_row, y2_lo_off;
   int ksplit;        // > 1: gridDim.y CTAs share one row tile, each reduces a slice of the contraction and adds its
@@ -390,6 +391,21 @@ __global__ void __launch_bounds__(kThreads) umma_gather_gemm_kernel(const GGPara
           }
         }
         const bool vec = (col0 + 16 <= p.cout) && ((p.cout & 3) == 0);
+        if (p.act >= 2) {
+          // backward-pass epilogues of the SDF decoder (y2 is an INPUT here, plain fp32, row stride y2_row):
+          //   2: y = v * 100 s (1 - s)       (through the softplus derivative s = sigmoid(100 h))
+          //   3: y = y_old + v * s           4: y = y_old + v
+          const float* ar = reinterpret_cast<const float*>(p.y2) + j * p.y2_row + col0;
+          const float* yo = reinterpret_cast<const float*>(p.y) + j * p.y_row + col0;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            if (col0 + i < p.cout) {
+              if (p.act == 2) { const float sg = __ldg(ar + i); f[i] *= 100.f * sg * (1.f - sg); }
+              else if (p.act == 3) f[i] = yo[i] + f[i] * __ldg(ar + i);
+              else f[i] += yo[i];
+            }
+          }
+        }
         if (p.ksplit > 1) {
           float* yr = reinterpret_cast<float*>(p.y) + j * p.y_row + col0;
           if (n_active > 0) {
@@ -518,7 +534,7 @@ int launch(const GGParams& p0, cudaStream_t stream) {
   }
   const unsigned tiles = (unsigned)((p.n_out + kTileM - 1) / kTileM);
   int ksplit = 1;
-  if (kSplit && !p.y_split && p.act == 0 && tiles * 2 <= PV2_SM_COUNT && p.num_chunks >= 16) {
+  if (kSplit && !p.y_split && p.act == 0 && tiles * 2 <= PV2_SM_COUNT && p.num_chunks >= 16) {  // (act: one writer per row)
     ksplit = (PV2_SM_COUNT + (int)tiles - 1) / (int)tiles;  // ~one CTA per SM in total
     if (ksplit > p.num_chunks / 8) ksplit = p.num_chunks / 8;
     if (ksplit < 1) ksplit = 1;
@@ -595,7 +611,9 @@ int pv2_linear(const float* x, int64_t x_row, int64_t x_lo_off, int x_presplit, 
                int64_t y2_lo_off, int64_t rows, int cin, int cout, void* workspace, size_t workspace_bytes,
                void* stream_) {
   (void)workspace; (void)workspace_bytes;
-  PV2_CHECK_ARG(rows >= 0 && cin > 0 && cout > 0 && cout <= 256 && (cin % 4) == 0 && act >= 0 && act <= 1);
+  PV2_CHECK_ARG(rows >= 0 && cin > 0 && cout > 0 && cout <= 256 && (cin % 4) == 0 && act >= 0 && act <= 4);
+  PV2_CHECK_ARG((act != 2 && act != 3) || y2 != nullptr);
+  PV2_CHECK_ARG(act < 2 || !y_split);
   if (rows == 0) return 0;
   PV2_CHECK_ARG(x && w && y);
   PV2_CHECK_ARG((x_row % 4) == 0 && (x_lo_off % 4) == 0 && (((uintptr_t)x | (uintptr_t)w | (uintptr_t)y) & 15) == 0);

@@ -127,37 +127,35 @@ class FusedFieldFunction(torch.autograd.Function):
         dF = torch.empty((P, 128), dtype=torch.float32, device=dev)
         doutbar = torch.empty((P, 68), dtype=torch.float32, device=dev)
         ubar = torch.empty((P, 64), dtype=torch.float32, device=dev)
-        dMr = torch.zeros((3, 134), dtype=torch.float32, device=dev)
-        dcr = torch.zeros(3, dtype=torch.float32, device=dev)
+        small = torch.zeros(3 * 134 + 3 + 64 + 68, dtype=torch.float32, device=dev)   # one fill for the four accumulators
+        dMr, dcr = small[:402].view(3, 134), small[402:405]
+        d_m10, d_c1 = small[405:469], small[469:537]
         sp = _lib.stream_ptr
         with torch.cuda.device(dev):
             _lib.check(lib.pv2_field_post_bwd(_lib.ptr(vol_cl), _lib.ptr(pts), _lib.ptr(dirs), ctx.spr, _lib.ptr(f_r),
                                               _lib.C.c_void_p(out.data_ptr() + 4), 68, _lib.ptr(grad), _lib.ptr(rgb),
                                               _lib.ptr(Mr), _lib.ptr(g_rgb), _lib.ptr(g_grad), _lib.ptr(g_sdf), P, Z, Y,
                                               X, C, _lib.ptr(gbar), _lib.ptr(dF), 128, _lib.ptr(doutbar), _lib.ptr(ubar),
-                                              _lib.ptr(dMr), _lib.ptr(dcr), sp()), "pv2_field_post_bwd")
-        # through u = s wp^T + m10
-        sbar = torch.empty((P, 128), dtype=torch.float32, device=dev)
-        _linear(ubar, 64, 0, False, wp.t().contiguous(), None, sbar, 128, 0, False, 0, None, 0, 0, P, 64, 128)
+                                              _lib.ptr(dMr), _lib.ptr(dcr), _lib.ptr(d_m10), _lib.ptr(d_c1), sp()),
+                       "pv2_field_post_bwd")
+        # through u = s wp^T + m10, then through s = sigmoid(100 h):  hbar = (ubar wp^T) * 100 s (1 - s)   [epilogue 2]
+        hbar = torch.empty((P, 128), dtype=torch.float32, device=dev)
+        _linear(ubar, 64, 0, False, wp.t().contiguous(), None, hbar, 128, 0, False, 2, s, 128, 0, P, 64, 128)
         d_wp = _dense_wgrad(s, 128, 0, ubar, 64, 0, P, 128, 64)
-        d_m10 = ubar.sum(0)
-        hbar = sbar * (100.0 * s * (1.0 - s))
-        # through out = [a | f_s] wcat^T + c1
-        xabar = torch.empty((P, 192), dtype=torch.float32, device=dev)
-        _linear(doutbar, 68, 0, False, wcat.t().contiguous(), None, xabar, 192, 0, False, 0, None, 0, 0, P, 68, 192)
+        # through out = [a | f_s] wcat^T + c1:  hbar += (doutbar wcat[:, :128]) * s   [epilogue 3];  dF[:, :64] = doutbar wcat[:, 128:]
+        wcat_t = wcat.t().contiguous()                                    # [192, 68]
+        _linear(doutbar, 68, 0, False, wcat_t[:128], None, hbar, 128, 0, False, 3, s, 128, 0, P, 68, 128)
+        _linear(doutbar, 68, 0, False, wcat_t[128:], None, dF, 128, 0, False, 0, None, 0, 0, P, 68, 64)
         d_wcat = _dense_wgrad(xa, 192, 0, doutbar, 68, 0, P, 192, 68)
-        d_c1 = doutbar.sum(0)
-        # through a = softplus(h), h = f_s M0^T + c0
-        hbar = hbar + xabar[:, :128] * s
-        _linear(hbar, 128, 0, False, M0.t().contiguous(), None, dF, 128, 0, False, 0, None, 0, 0, P, 128, 64)
-        dF[:, :64] += xabar[:, 128:]
+        # through a = softplus(h), h = f_s M0^T + c0:  dF[:, :64] += hbar M0   [epilogue 4]
+        _linear(hbar, 128, 0, False, M0.t().contiguous(), None, dF, 128, 0, False, 4, None, 0, 0, P, 128, 64)
         d_M0 = _dense_wgrad(xa[:, 128:], 192, 0, hbar, 128, 0, P, 64, 128)
         d_c0 = hbar.sum(0)
         dvol = torch.zeros_like(vol_cl)
         with torch.cuda.device(dev):
             _lib.check(lib.pv2_field_sample_bwd(_lib.ptr(pts), _lib.ptr(dF), 128, _lib.ptr(u), _lib.ptr(gbar), P, Z, Y, X,
                                                 C, 64, _lib.ptr(dvol), sp()), "pv2_field_sample_bwd")
-        return dvol, None, None, None, d_M0, d_c0, d_wcat, d_c1, d_wp, d_m10, dMr, dcr
+        return dvol, None, None, None, d_M0, d_c0, d_wcat, d_c1.clone(), d_wp, d_m10.clone(), dMr.clone(), dcr.clone()
 
 
 def fold_parameters(field) -> dict:
