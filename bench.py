@@ -135,6 +135,24 @@ def host_threads() -> int:
     return max(1, min(os.cpu_count() or 1, 32))
 
 
+def profiled_traffic(kernel_prefix: str):
+    """DRAM bytes per launch of `kernel_prefix` from the newest committed ncu launch list (profiles/*_traffic.json,
+    written by tools/traffic_from_launches.py); None when no profile has been committed."""
+    best = None
+    for f in sorted((ROOT / "profiles").glob("*_traffic.json")):
+        try:
+            d = json.loads(f.read_text())
+        except ValueError:
+            continue
+        tot_b = tot_n = 0
+        for name, v in d.get("kernels", {}).items():
+            if name.startswith(kernel_prefix):
+                tot_b += v["dram_bytes_total"]; tot_n += v["launches"]
+        if tot_n:
+            best = dict(bytes_per_launch=tot_b / tot_n, source=f"profiles/{f.name}")
+    return best
+
+
 def measured_peaks() -> dict:
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -325,6 +343,7 @@ def run_ours(args, wl: dict) -> None:
         peaks = measured_peaks()
         gg = prof.get("pv2_spconv_gather_gemm", dict(calls=0, ms=0.0, bytes=0))
         achieved = gg["bytes"] / max(gg["ms"], 1e-9) * 1e-6 if gg["calls"] else 0.0  # GB/s
+        traffic = profiled_traffic("umma_gather_gemm_kernel")
         line = {
             "metric": "pretrain_rays_per_sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
@@ -338,7 +357,11 @@ def run_ours(args, wl: dict) -> None:
             "gpu_launches": int(launches),
             "roofline": {"kernel": "pv2_spconv_gather_gemm (fwd + dgrad, all layers)", "bound": "hbm",
                          "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
+                         "frac": achieved / peaks["hbm_gbs"],
+                         "traffic": traffic["bytes_per_launch"] if traffic else None,
+                         "traffic_source": traffic["source"] if traffic else None,
+                         "algorithmic_bytes_per_launch": gg["bytes"] / max(gg["calls"], 1),
+                         "peak_source": peaks["source"],
                          "launches": gg["calls"], "kernel_ms_per_step": gg["ms"] / args.steps,
                          "share_of_step": gg["ms"] / max(ms_dev, 1e-9)},
             "kernel_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()},

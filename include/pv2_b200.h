@@ -121,6 +121,23 @@ int pv2_spconv_wgrad(const void* x, const void* dy, const int32_t* nbr, const in
 size_t pv2_wgrad_workspace_bytes(int64_t n_in, int64_t n_out, int cin, int cout);
 
 /* ------------------------------------------------------------------------------------------
+ * BatchNorm1d with batch statistics (+ residual add, + ReLU) over [n, c] voxel features, c % 4 == 0:
+ * the conv -> bn -> relu / conv -> bn -> (+ residual) -> relu chains of spconv_unet_v1m1_base.py:70-83,111-180.
+ *   y = [relu]((x - mean) * invstd * gamma + beta [+ res]);  mean / invstd [c] are outputs (saved for backward);
+ *   running_mean / running_var (optional) are updated with torch's semantics (momentum, unbiased variance).
+ * Backward: dz = dy * (y > 0 if relu); dgamma = sum dz * xhat; dbeta = sum dz;
+ *   dx = gamma * invstd * (dz - dbeta / n - xhat * dgamma / n);  dres (optional) = dz.
+ * Deterministic (per-block partial sums combined in double; no atomics).
+ * ------------------------------------------------------------------------------------------ */
+size_t pv2_bn_workspace_bytes(int64_t n, int c);
+int pv2_bn_act_fwd(const float* x, const float* res, const float* gamma, const float* beta, float* running_mean,
+                   float* running_var, float momentum, float eps, int relu, int64_t n, int c, float* y, float* mean,
+                   float* invstd, void* workspace, size_t workspace_bytes, void* stream);
+int pv2_bn_act_bwd(const float* x, const float* dy, const float* y, const float* gamma, const float* mean,
+                   const float* invstd, int relu, int64_t n, int c, float* dx, float* dres, float* dgamma, float* dbeta,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Densify: voxel features -> dense channels-last volume, scatter-mean
  * (ponder_indoor_base.py:177-216,332-342; ponder_outdoor_base.py:178-210).
  * cell: [n] int64 flattened cell id in the OUTPUT memory order, or -1 to drop the row.

@@ -55,6 +55,9 @@ SIGNATURES = {
                                       _vp, _vp, _vp, _vp, _vp]),
     "pv2_ray_loss_fwd": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, C.c_float, _vp, _vp]),
     "pv2_ray_loss_bwd": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, C.c_float, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pv2_bn_workspace_bytes": (_sz, [_i64, _int]),
+    "pv2_bn_act_fwd": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_float, C.c_float, _int, _i64, _int, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "pv2_bn_act_bwd": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _i64, _int, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pv2_densify_fwd": (_int, [_vp, _vp, _i64, _int, _i64, _vp, _vp, _vp]),
     "pv2_densify_bwd": (_int, [_vp, _vp, _vp, _i64, _int, _vp, _vp]),
     "pv2_trilinear_fwd": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _int, _int, _int, _int, _vp]),

@@ -15,6 +15,7 @@ import torch
 from torch import nn
 
 from . import _lib
+from .bn_act import bn_act
 from .spconv import pytorch as spconv
 
 
@@ -56,12 +57,24 @@ class ResidualBlock(spconv.SparseModule):
         self.stride = stride
 
     def forward(self, x):
+        # conv - bn - relu - conv - bn - (+ residual) - relu, with each bn(+add)+relu a fused kernel pair (bn_act.py)
         out = self.conv1(x)
-        out = out.replace_feature(self.relu(self.bn1(out.features)))
+        out = out.replace_feature(bn_act(out.features, self.bn1, None, True))
         out = self.conv2(out)
-        out = out.replace_feature(self.bn2(out.features))
-        out = out.replace_feature(self.relu(out.features + self.proj(x).features))
-        return out
+        if len(self.proj) == 2:   # 1x1 projection + its own BatchNorm (no ReLU)
+            res = bn_act(self.proj[0](x).features, self.proj[1], None, False)
+        else:
+            res = x.features
+        return out.replace_feature(bn_act(out.features, self.bn2, res, True))
+
+
+class ConvBNReLU(spconv.SparseSequential):
+    """SparseSequential(conv, BatchNorm1d, ReLU) — same children / state_dict keys ('0', '1', '2') as the reference's
+    blocks (spconv_unet_v1m1_base.py:111-119,134-145,170-180) — with the BatchNorm + ReLU pair run as one fused op."""
+
+    def forward(self, input):
+        out = self[0](input)
+        return out.replace_feature(bn_act(out.features, self[1], None, True))
 
 
 class SpUNetBase(nn.Module):
@@ -77,21 +90,21 @@ class SpUNetBase(nn.Module):
         self.cls_mode = cls_mode
         norm_fn = partial(nn.BatchNorm1d, eps=1e-3, momentum=0.01)
 
-        self.conv_input = spconv.SparseSequential(
+        self.conv_input = ConvBNReLU(
             spconv.SubMConv3d(in_channels, base_channels, kernel_size=5, padding=1, bias=False, indice_key="stem"),
             norm_fn(base_channels), nn.ReLU())
         self.down, self.up, self.enc, self.dec = nn.ModuleList(), nn.ModuleList(), nn.ModuleList(), nn.ModuleList()
         enc_c, dec_c = base_channels, channels[-1]
         nch = len(channels)
         for s in range(self.num_stages):
-            self.down.append(spconv.SparseSequential(
+            self.down.append(ConvBNReLU(
                 spconv.SparseConv3d(enc_c, channels[s], kernel_size=2, stride=2, bias=False,
                                     indice_key=f"spconv{s + 1}"),
                 norm_fn(channels[s]), nn.ReLU()))
             self.enc.append(spconv.SparseSequential(OrderedDict(
                 (f"block{i}", ResidualBlock(channels[s], channels[s], norm_fn=norm_fn, indice_key=f"subm{s + 1}"))
                 for i in range(layers[s]))))
-            self.up.append(spconv.SparseSequential(
+            self.up.append(ConvBNReLU(
                 spconv.SparseInverseConv3d(channels[nch - s - 2], dec_c, kernel_size=2, bias=False,
                                            indice_key=f"spconv{s + 1}"),
                 norm_fn(dec_c), nn.ReLU()))
@@ -115,6 +128,26 @@ class SpUNetBase(nn.Module):
             nn.init.constant_(m.bias, 0)
             nn.init.constant_(m.weight, 1.0)
 
+    def _prebuild_rulebooks(self, x: "spconv.SparseConvTensor") -> None:
+        """All coordinate work of the step up front.  The rulebooks depend on coordinates only, and each strided one
+        ends in a host read of its output count (tensor shapes depend on it); built lazily inside the layer stack
+        those four syncs drain a full launch queue each.  Built here, nothing is queued behind them yet and the host
+        runs ahead of the GPU for the rest of the forward pass.  Keys are the reference's indice_keys
+        (spconv_unet_v1m1_base.py:111-177): stem (k5), subm0..4 (k3), spconv1..4 (k2 s2)."""
+        d = x.indice_dict
+        ind, shape = x.indices, x.spatial_shape
+        if "stem" not in d:
+            d["stem"] = spconv.build_subm_rulebook(ind, shape, self.conv_input[0].kernel_size[0], count_pairs=False)
+        if "subm0" not in d:
+            d["subm0"] = spconv.build_subm_rulebook(ind, shape, 3, count_pairs=False)
+        for s in range(self.num_stages):
+            key = f"spconv{s + 1}"
+            if key not in d:
+                d[key] = spconv.build_down_rulebook(ind, shape)
+            ind, shape = d[key].out_indices, d[key].out_shape
+            if f"subm{s + 1}" not in d:
+                d[f"subm{s + 1}"] = spconv.build_subm_rulebook(ind, shape, 3, count_pairs=False)
+
     def forward(self, input_dict):
         grid_coord, feat, offset = input_dict["grid_coord"], input_dict["feat"], input_dict["offset"]
         if not grid_coord.is_cuda:
@@ -124,6 +157,7 @@ class SpUNetBase(nn.Module):
             shape = torch.add(torch.max(grid_coord, dim=0).values, 96).tolist()
         x = spconv.SparseConvTensor(features=feat, indices=make_sparse_indices(grid_coord, offset),
                                     spatial_shape=shape, batch_size=int(offset.shape[0]))
+        self._prebuild_rulebooks(x)
         x = self.conv_input(x)
         skips = [x]
         for s in range(self.num_stages):

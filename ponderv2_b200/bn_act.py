@@ -1,0 +1,81 @@
+"""Fused BatchNorm1d (+ residual) (+ ReLU) for voxel features (csrc/bn_act.cu) — row a6 of the hot path.
+
+`bn_act(x, bn, residual=None, relu=True)` applies the `nn.BatchNorm1d` module `bn` exactly as
+`relu(bn(x) + residual)` would (reference: BasicBlock.forward, spconv_unet_v1m1_base.py:70-83, and the conv-bn-relu
+blocks :111-180): batch statistics in training mode with the running buffers updated in place (momentum, unbiased
+variance, num_batches_tracked), so state_dicts stay interchangeable with the reference's.  Two kernels forward, two
+backward instead of torch's five and eight passes.  Eval mode (running statistics) is a plain affine map and stays torch.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import _lib
+
+
+class _BNActFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, res, gamma, beta, running_mean, running_var, momentum: float, eps: float, relu: bool):
+        lib = _lib.load()
+        x = x.contiguous()
+        n, c = x.shape
+        dev = x.device
+        res_c = res.contiguous() if res is not None else None
+        y = torch.empty_like(x)
+        stats = torch.empty((2, c), dtype=torch.float32, device=dev)
+        ws_bytes = lib.pv2_bn_workspace_bytes(n, c)
+        ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.pv2_bn_act_fwd(_lib.ptr(x), _lib.ptr(res_c), _lib.ptr(gamma.contiguous()),
+                                          _lib.ptr(beta.contiguous()), _lib.ptr(running_mean), _lib.ptr(running_var),
+                                          float(momentum), float(eps), int(relu), n, c, _lib.ptr(y), _lib.ptr(stats[0]),
+                                          _lib.ptr(stats[1]), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
+                       "pv2_bn_act_fwd")
+        ctx.save_for_backward(x, y, gamma, stats)
+        ctx.relu, ctx.has_res = bool(relu), res is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y, gamma, stats = ctx.saved_tensors
+        lib = _lib.load()
+        n, c = x.shape
+        dev = x.device
+        dy = dy.contiguous()
+        dx = torch.empty_like(x)
+        dres = torch.empty_like(x) if ctx.has_res else None
+        dgb = torch.empty((2, c), dtype=torch.float32, device=dev)
+        ws_bytes = lib.pv2_bn_workspace_bytes(n, c)
+        ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.pv2_bn_act_bwd(_lib.ptr(x), _lib.ptr(dy), _lib.ptr(y), _lib.ptr(gamma.contiguous()),
+                                          _lib.ptr(stats[0]), _lib.ptr(stats[1]), int(ctx.relu), n, c, _lib.ptr(dx),
+                                          _lib.ptr(dres), _lib.ptr(dgb[0]), _lib.ptr(dgb[1]), _lib.ptr(ws), ws.numel(),
+                                          _lib.stream_ptr()), "pv2_bn_act_bwd")
+        return dx, dres, dgb[0], dgb[1], None, None, None, None, None
+
+
+def supported(x: torch.Tensor, bn: nn.BatchNorm1d) -> bool:
+    return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.shape[0] > 1 and x.shape[1] % 4 == 0
+            and x.shape[1] <= 1024 and bn.affine and bn.weight.dtype == torch.float32)
+
+
+def bn_act(x: torch.Tensor, bn: nn.BatchNorm1d, residual: Optional[torch.Tensor] = None, relu: bool = True) -> torch.Tensor:
+    """relu(bn(x) + residual) with `bn` an nn.BatchNorm1d (its parameters and running buffers are used / updated)."""
+    if bn.training and supported(x, bn):
+        momentum = bn.momentum
+        if bn.track_running_stats and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+            if momentum is None:  # cumulative moving average
+                momentum = 1.0 / float(bn.num_batches_tracked)
+        rm = bn.running_mean if bn.track_running_stats else None
+        rv = bn.running_var if bn.track_running_stats else None
+        return _BNActFunction.apply(x, residual, bn.weight, bn.bias, rm, rv, float(momentum or 0.0), float(bn.eps), relu)
+    out = bn(x)
+    if residual is not None:
+        out = out + residual
+    return F.relu(out) if relu else out

@@ -1,0 +1,206 @@
+// BatchNorm1d (batch statistics) + optional residual add + optional ReLU over [N, C] voxel features, forward and
+// backward: row a6 of the hot path (ponder/models/sparse_unet/spconv_unet_v1m1_base.py:70-83 `BasicBlock.forward`:
+// conv -> bn -> relu -> conv -> bn -> (+ residual) -> relu, and the conv -> bn -> relu stems/down/up blocks :111-180).
+//
+// torch runs this as BN-stats, BN-apply, add, ReLU forward (5 passes over [N, C]) and ReLU-bwd, BN-reduce, BN-apply
+// backward (8 passes).  Here: forward = one statistics pass + one fused apply pass (normalise, affine, + residual, ReLU);
+// backward = one reduction pass (d gamma, d beta with the ReLU mask applied on the fly) + one fused apply pass that
+// writes dx and the residual gradient.  Pure HBM-bound elementwise/reduction work: float4 accesses, per-block partial
+// sums combined in double by a one-block finalize kernel (no atomics, deterministic).
+#include "pv2_common.cuh"
+
+namespace {
+
+constexpr int kRowsPerBlock = 256;
+constexpr int kBnThreads = 256;
+
+// Per-block column sums of up to two quantities.  Thread t owns channel group (t % C4) and rows (t / C4) + i * RP.
+// MODE 0: (x, x*x).  MODE 1: (dz, dz * xhat) with dz = dy * (y > 0 if relu), xhat = (x - mean) * invstd.
+template <int MODE>
+__global__ void __launch_bounds__(kBnThreads) bn_partial_kernel(const float4* __restrict__ x, const float4* __restrict__ dy,
+                                                                const float4* __restrict__ y, const float* __restrict__ mean,
+                                                                const float* __restrict__ invstd, int64_t N, int C4, int relu,
+                                                                float4* __restrict__ partial /*[nblk][2][C4]*/) {
+  __shared__ float4 sa[kBnThreads], sb[kBnThreads];
+  const int tid = threadIdx.x;
+  const int RP = kBnThreads / C4;          // rows per pass
+  const int cg = tid % C4, rt = tid / C4;
+  const bool active = rt < RP;
+  const int64_t row0 = (int64_t)blockIdx.x * kRowsPerBlock;
+  int64_t rows = N - row0;
+  if (rows > kRowsPerBlock) rows = kRowsPerBlock;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+  float4 mu = a, is = a;
+  if (MODE == 1 && active) {
+    mu = *reinterpret_cast<const float4*>(mean + cg * 4);
+    is = *reinterpret_cast<const float4*>(invstd + cg * 4);
+  }
+  if (active) {
+    for (int64_t r = rt; r < rows; r += RP) {
+      const int64_t e = (row0 + r) * C4 + cg;
+      const float4 v = __ldg(&x[e]);
+      if (MODE == 0) {
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        b.x = fmaf(v.x, v.x, b.x); b.y = fmaf(v.y, v.y, b.y); b.z = fmaf(v.z, v.z, b.z); b.w = fmaf(v.w, v.w, b.w);
+      } else {
+        float4 g = __ldg(&dy[e]);
+        if (relu) {
+          const float4 o = __ldg(&y[e]);
+          g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f; g.z = o.z > 0.f ? g.z : 0.f; g.w = o.w > 0.f ? g.w : 0.f;
+        }
+        a.x += g.x; a.y += g.y; a.z += g.z; a.w += g.w;
+        b.x = fmaf(g.x, (v.x - mu.x) * is.x, b.x); b.y = fmaf(g.y, (v.y - mu.y) * is.y, b.y);
+        b.z = fmaf(g.z, (v.z - mu.z) * is.z, b.z); b.w = fmaf(g.w, (v.w - mu.w) * is.w, b.w);
+      }
+    }
+  }
+  sa[tid] = a; sb[tid] = b;
+  __syncthreads();
+  if (tid < C4) {
+    float4 ta = sa[tid], tb = sb[tid];
+    for (int r = 1; r < RP; ++r) {
+      const float4 u = sa[r * C4 + tid], w = sb[r * C4 + tid];
+      ta.x += u.x; ta.y += u.y; ta.z += u.z; ta.w += u.w;
+      tb.x += w.x; tb.y += w.y; tb.z += w.z; tb.w += w.w;
+    }
+    partial[((int64_t)blockIdx.x * 2) * C4 + tid] = ta;
+    partial[((int64_t)blockIdx.x * 2 + 1) * C4 + tid] = tb;
+  }
+}
+
+// one thread per channel: combine the per-block partial sums in double
+// MODE 0: mean / invstd (+ running statistics, torch semantics: momentum, unbiased running variance)
+// MODE 1: dgamma = sum dz * xhat, dbeta = sum dz
+template <int MODE>
+__global__ void bn_finalize_kernel(const float* __restrict__ partial, int nblk, int C, int64_t N, float eps, float momentum,
+                                   float* __restrict__ out_a, float* __restrict__ out_b, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double sa = 0.0, sb = 0.0;
+  for (int b = 0; b < nblk; ++b) {
+    sa += (double)partial[((int64_t)b * 2) * C + c];
+    sb += (double)partial[((int64_t)b * 2 + 1) * C + c];
+  }
+  if (MODE == 0) {
+    const double m = sa / (double)N;
+    double var = sb / (double)N - m * m;
+    if (var < 0.0) var = 0.0;
+    out_a[c] = (float)m;
+    out_b[c] = (float)(1.0 / sqrt(var + (double)eps));
+    if (running_mean != nullptr) {
+      const double unb = N > 1 ? var * (double)N / (double)(N - 1) : var;
+      running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * m);
+      running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unb);
+    }
+  } else {
+    out_a[c] = (float)sb;   // dgamma
+    out_b[c] = (float)sa;   // dbeta
+  }
+}
+
+// y = [relu]((x - mean) * invstd * gamma + beta [+ res])
+__global__ void bn_apply_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ res, const float* __restrict__ mean,
+                                    const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                    const float* __restrict__ beta, int64_t total4, int C4, int relu, float4* __restrict__ y) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % C4);
+    const float4 mu = *reinterpret_cast<const float4*>(mean + cg * 4);
+    const float4 is = *reinterpret_cast<const float4*>(invstd + cg * 4);
+    const float4 ga = *reinterpret_cast<const float4*>(gamma + cg * 4);
+    const float4 be = *reinterpret_cast<const float4*>(beta + cg * 4);
+    const float4 v = __ldg(&x[i]);
+    float4 o;
+    o.x = (v.x - mu.x) * is.x * ga.x + be.x; o.y = (v.y - mu.y) * is.y * ga.y + be.y;
+    o.z = (v.z - mu.z) * is.z * ga.z + be.z; o.w = (v.w - mu.w) * is.w * ga.w + be.w;
+    if (res != nullptr) { const float4 r = __ldg(&res[i]); o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w; }
+    if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+    y[i] = o;
+  }
+}
+
+// dz = dy * (y > 0 if relu);  dx = gamma * invstd * (dz - dbeta / N - xhat * dgamma / N);  dres = dz
+__global__ void bn_apply_bwd_kernel(const float4* __restrict__ x, const float4* __restrict__ dy, const float4* __restrict__ y,
+                                    const float* __restrict__ mean, const float* __restrict__ invstd,
+                                    const float* __restrict__ gamma, const float* __restrict__ dgamma,
+                                    const float* __restrict__ dbeta, int64_t total4, int C4, int relu, float inv_n,
+                                    float4* __restrict__ dx, float4* __restrict__ dres) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % C4);
+    const float4 mu = *reinterpret_cast<const float4*>(mean + cg * 4);
+    const float4 is = *reinterpret_cast<const float4*>(invstd + cg * 4);
+    const float4 ga = *reinterpret_cast<const float4*>(gamma + cg * 4);
+    const float4 dg = *reinterpret_cast<const float4*>(dgamma + cg * 4);
+    const float4 db = *reinterpret_cast<const float4*>(dbeta + cg * 4);
+    const float4 v = __ldg(&x[i]);
+    float4 g = __ldg(&dy[i]);
+    if (relu) {
+      const float4 o = __ldg(&y[i]);
+      g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f; g.z = o.z > 0.f ? g.z : 0.f; g.w = o.w > 0.f ? g.w : 0.f;
+    }
+    if (dres != nullptr) dres[i] = g;
+    float4 d;
+    d.x = ga.x * is.x * (g.x - db.x * inv_n - (v.x - mu.x) * is.x * dg.x * inv_n);
+    d.y = ga.y * is.y * (g.y - db.y * inv_n - (v.y - mu.y) * is.y * dg.y * inv_n);
+    d.z = ga.z * is.z * (g.z - db.z * inv_n - (v.z - mu.z) * is.z * dg.z * inv_n);
+    d.w = ga.w * is.w * (g.w - db.w * inv_n - (v.w - mu.w) * is.w * dg.w * inv_n);
+    dx[i] = d;
+  }
+}
+
+inline int nblocks_for(int64_t n) { return (int)((n + kRowsPerBlock - 1) / kRowsPerBlock); }
+inline bool shape_ok(int64_t n, int c) { return n >= 0 && c >= 4 && c <= 1024 && (c % 4) == 0 && (kBnThreads / (c / 4)) >= 1; }
+
+}  // namespace
+
+extern "C" {
+
+size_t pv2_bn_workspace_bytes(int64_t n, int c) {
+  if (!shape_ok(n, c)) return 0;
+  return ((size_t)nblocks_for(n) * 2 * c * sizeof(float) + 255) / 256 * 256;
+}
+
+int pv2_bn_act_fwd(const float* x, const float* res, const float* gamma, const float* beta, float* running_mean,
+                   float* running_var, float momentum, float eps, int relu, int64_t n, int c, float* y, float* mean,
+                   float* invstd, void* workspace, size_t workspace_bytes, void* stream_) {
+  PV2_CHECK_ARG(shape_ok(n, c));
+  if (n == 0) return 0;
+  PV2_CHECK_ARG(x && gamma && beta && y && mean && invstd && workspace);
+  PV2_CHECK_ARG((((uintptr_t)x | (uintptr_t)y | (uintptr_t)res | (uintptr_t)mean | (uintptr_t)invstd | (uintptr_t)gamma |
+                  (uintptr_t)beta) & 15) == 0);
+  if (workspace_bytes < pv2_bn_workspace_bytes(n, c)) return PV2_EWORKSPACE;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int nblk = nblocks_for(n), C4 = c / 4;
+  bn_partial_kernel<0><<<nblk, kBnThreads, 0, stream>>>((const float4*)x, nullptr, nullptr, nullptr, nullptr, n, C4, 0,
+                                                         (float4*)workspace);
+  bn_finalize_kernel<0><<<(c + 127) / 128, 128, 0, stream>>>((const float*)workspace, nblk, c, n, eps, momentum, mean, invstd,
+                                                             running_mean, running_var);
+  const int64_t total4 = n * C4;
+  bn_apply_fwd_kernel<<<pv2_grid_for(total4, 256), 256, 0, stream>>>((const float4*)x, (const float4*)res, mean, invstd, gamma, beta,
+                                                                    total4, C4, relu, (float4*)y);
+  PV2_DONE(3);
+}
+
+int pv2_bn_act_bwd(const float* x, const float* dy, const float* y, const float* gamma, const float* mean,
+                   const float* invstd, int relu, int64_t n, int c, float* dx, float* dres, float* dgamma, float* dbeta,
+                   void* workspace, size_t workspace_bytes, void* stream_) {
+  PV2_CHECK_ARG(shape_ok(n, c));
+  if (n == 0) return 0;
+  PV2_CHECK_ARG(x && dy && gamma && mean && invstd && dx && dgamma && dbeta && workspace && (!relu || y));
+  PV2_CHECK_ARG((((uintptr_t)x | (uintptr_t)dy | (uintptr_t)y | (uintptr_t)dx | (uintptr_t)dres | (uintptr_t)mean |
+                  (uintptr_t)invstd | (uintptr_t)gamma | (uintptr_t)dgamma | (uintptr_t)dbeta) & 15) == 0);
+  if (workspace_bytes < pv2_bn_workspace_bytes(n, c)) return PV2_EWORKSPACE;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int nblk = nblocks_for(n), C4 = c / 4;
+  bn_partial_kernel<1><<<nblk, kBnThreads, 0, stream>>>((const float4*)x, (const float4*)dy, (const float4*)y, mean, invstd, n, C4,
+                                                         relu, (float4*)workspace);
+  bn_finalize_kernel<1><<<(c + 127) / 128, 128, 0, stream>>>((const float*)workspace, nblk, c, n, 0.f, 0.f, dgamma, dbeta, nullptr,
+                                                             nullptr);
+  const int64_t total4 = n * C4;
+  bn_apply_bwd_kernel<<<pv2_grid_for(total4, 256), 256, 0, stream>>>((const float4*)x, (const float4*)dy, (const float4*)y, mean,
+                                                                    invstd, gamma, dgamma, dbeta, total4, C4, relu,
+                                                                    1.0f / (float)n, (float4*)dx, (float4*)dres);
+  PV2_DONE(3);
+}
+
+}  // extern "C"

@@ -52,6 +52,7 @@ struct GGParams {
   int stages;
   uint32_t tmem_cols;
   int64_t x_row;     // elements between consecutive rows of x
+  uint32_t x_row32, w_sco32, w_sk32;   // the same strides as 32-bit factors (one IMAD.WIDE.U32 per address)
   int64_t x_lo_off;  // fp32: != 0 -> x is split-precision, value = x[..] + x[.. + x_lo_off]
   // output: row stride, optional split-precision output (hi at y, lo at y + y_lo_off) and the fused epilogue
   int64_t y_row, y_lo_off;
@@ -130,6 +131,7 @@ __global__ void __launch_bounds__(kThreads) umma_gather_gemm_kernel(const GGPara
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 1);
   uint32_t* kmask_s = tmem_slot + 1;                       // [4]: one bit per kernel offset (K <= 128)
   int* wcount_s = reinterpret_cast<int*>(tmem_slot + 5);  // [kProducerWarps + 1]
+  uint32_t* kc_s = reinterpret_cast<uint32_t*>(wcount_s + kProducerWarps + 1);   // [num_chunks][8]: (k << 16 | ci) per 16-byte piece
 
   // ---- setup ---------------------------------------------------------------------------------------------
   if (tid < kTileM) {
@@ -173,6 +175,16 @@ __global__ void __launch_bounds__(kThreads) umma_gather_gemm_kernel(const GGPara
         const int i = i0 + u * kThreads;
         if (i < total) idx_s[i] = v[u];
       }
+    }
+  }
+  // (offset, channel) of every 16-byte piece of every chunk, computed once (the divisions stay out of the main loop)
+  {
+    const int ktot_ = p.kvol * p.cin;
+    for (int i = tid; i < p.num_chunks * 8; i += kThreads) {
+      const int e0 = (i >> 3) * T::kEPR + (i & 7) * T::kEPP;
+      uint32_t v = 0xffffffffu;
+      if (e0 < ktot_) { const int k = e0 / p.cin; v = ((uint32_t)k << 16) | (uint32_t)(e0 - k * p.cin); }
+      kc_s[i] = v;
     }
   }
   __syncthreads();
@@ -230,7 +242,6 @@ __global__ void __launch_bounds__(kThreads) umma_gather_gemm_kernel(const GGPara
     if (q >= n_total) q -= n_total;
     return (int)active[q];
   };
-  const int ktot = p.kvol * p.cin;
 
   if (warp < kProducerWarps) {
     // ======================= producers =======================
@@ -244,15 +255,17 @@ __global__ void __launch_bounds__(kThreads) umma_gather_gemm_kernel(const GGPara
       const int rbase = tg >> 3;       // 0..15; rows rbase + 16 i keep r & 7, so the swizzled offset advances 2048 B per i
       const uint32_t tile_off = sw128_offset(rbase, piece);
       const int nb = p.n_pad >> 4;     // weight rows per thread (1..16)
+      const float* wrow0 = w + (uint64_t)rbase * p.w_sco32;   // loop-invariant: weight row rbase
+      const uint64_t wstep = 16ull * p.w_sco32;                // rows rbase + 16 i
       const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int it = grp; it < n_active; it += 2) {
         const int c = chunk_at(it);
         const int s = it % p.stages;
         const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-        const int e0 = c * T::kEPR + piece * T::kEPP;
-        const bool kvalid = e0 < ktot;
-        const int k = kvalid ? e0 / p.cin : 0;
-        const int ci = kvalid ? e0 - k * p.cin : 0;
+        const uint32_t kc = kc_s[c * 8 + piece];
+        const bool kvalid = kc != 0xffffffffu;
+        const uint32_t k = kvalid ? kc >> 16 : 0u;
+        const uint32_t ci = kvalid ? (kc & 0xffffu) : 0u;
         const int32_t* idx_k = idx_s + k * kTileM;
         // every global load of the chunk is issued before anything waits
         float4 va[8];
@@ -261,7 +274,7 @@ __global__ void __launch_bounds__(kThreads) umma_gather_gemm_kernel(const GGPara
           const int32_t src = kvalid ? idx_k[rbase + 16 * i] : -1;
           va[i] = zero4;
           if (src >= 0) {
-            const float* g = x + ((int64_t)src * p.x_row + ci);
+            const float* g = x + ((uint64_t)(uint32_t)src * p.x_row32 + ci);
             va[i] = __ldg(reinterpret_cast<const float4*>(g));
           }
         }
@@ -271,18 +284,18 @@ __global__ void __launch_bounds__(kThreads) umma_gather_gemm_kernel(const GGPara
           for (int i = 0; i < 8; ++i) {
             const int32_t src = kvalid ? idx_k[rbase + 16 * i] : -1;
             vl[i] = zero4;
-            if (src >= 0) vl[i] = __ldg(reinterpret_cast<const float4*>(x + ((int64_t)src * p.x_row + ci) + p.x_lo_off));
+            if (src >= 0) vl[i] = __ldg(reinterpret_cast<const float4*>(x + ((uint64_t)(uint32_t)src * p.x_row32 + ci) + p.x_lo_off));
           }
 #pragma unroll
           for (int i = 0; i < 8; ++i) { va[i].x += vl[i].x; va[i].y += vl[i].y; va[i].z += vl[i].z; va[i].w += vl[i].w; }
         }
-        const float* wk = w + ((int64_t)k * p.w_sk + ci);
+        const float* wk = wrow0 + ((uint64_t)k * p.w_sk32 + ci);   // weight row rbase, this piece
         float4 vb[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int n = rbase + 16 * i;
           vb[i] = zero4;
-          if (kvalid && i < nb && n < p.cout) vb[i] = __ldg(reinterpret_cast<const float4*>(wk + (int64_t)n * p.w_sco));
+          if (kvalid && i < nb && n < p.cout) vb[i] = __ldg(reinterpret_cast<const float4*>(wk + (uint64_t)i * wstep));
         }
         mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
         const uint32_t a_dst = smem_u32(stage_base + (size_t)s * stage_bytes) + tile_off;
@@ -297,7 +310,7 @@ __global__ void __launch_bounds__(kThreads) umma_gather_gemm_kernel(const GGPara
           for (int i = 0; i < 8; ++i) {
             const int n = rbase + 16 * (i + 8);
             vb[i] = zero4;
-            if (kvalid && i + 8 < nb && n < p.cout) vb[i] = __ldg(reinterpret_cast<const float4*>(wk + (int64_t)n * p.w_sco));
+            if (kvalid && i + 8 < nb && n < p.cout) vb[i] = __ldg(reinterpret_cast<const float4*>(wk + (uint64_t)(i + 8) * wstep));
           }
 #pragma unroll
           for (int i = 0; i < 8; ++i)
@@ -310,7 +323,10 @@ __global__ void __launch_bounds__(kThreads) umma_gather_gemm_kernel(const GGPara
       const int piece = tid & 7;
       const int rbase = tid >> 3;      // 0..31; rows rbase + 32 i -> +4096 B per i
       const uint32_t tile_off = sw128_offset(rbase, piece);
-      const int lag = p.stages - 1;
+      // A stage is handed to the MMA warp `lag` iterations after its copies were issued and is refilled `stages`
+    // iterations later: lag = stages / 2 leaves the copies and the MMAs (issue -> commit -> barrier) about half of the
+    // ring each to complete in, instead of making every refill wait for MMAs issued one iteration earlier.
+    const int lag = p.stages >= 2 ? p.stages / 2 : 1;
       for (int it = 0; it < n_active + lag; ++it) {
         if (it < n_active) {
           const int c = chunk_at(it);
@@ -318,10 +334,10 @@ __global__ void __launch_bounds__(kThreads) umma_gather_gemm_kernel(const GGPara
           const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
           mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
           uint8_t* a_tile = stage_base + (size_t)s * stage_bytes;
-          const int e0 = c * T::kEPR + piece * T::kEPP;
-          const bool kvalid = e0 < ktot;
-          const int k = kvalid ? e0 / p.cin : 0;
-          const int ci = kvalid ? e0 - k * p.cin : 0;
+          const uint32_t kc = kc_s[c * 8 + piece];
+          const bool kvalid = kc != 0xffffffffu;
+          const uint32_t k = kvalid ? kc >> 16 : 0u;
+          const uint32_t ci = kvalid ? (kc & 0xffffu) : 0u;
           const int32_t* idx_k = idx_s + k * kTileM;
           int32_t src[4];
 #pragma unroll
@@ -329,14 +345,14 @@ __global__ void __launch_bounds__(kThreads) umma_gather_gemm_kernel(const GGPara
           const uint32_t a_dst = smem_u32(a_tile) + tile_off;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const E* g = (src[i] >= 0) ? x + ((int64_t)src[i] * p.x_row + ci) : x;
+            const E* g = (src[i] >= 0) ? x + ((uint64_t)(uint32_t)src[i] * p.x_row32 + ci) : x;
             cp_async_16(a_dst + i * 4096, g, src[i] >= 0 ? 16u : 0u);
           }
           const uint32_t b_dst = a_dst + kABytes;
-          const E* wk = w + ((int64_t)k * p.w_sk + ci);
+          const E* wk = w + ((uint64_t)rbase * p.w_sco32 + (uint64_t)k * p.w_sk32 + ci);
           for (int n = rbase, i = 0; n < p.n_pad; n += 32, ++i) {
             const bool ok = kvalid && n < p.cout;
-            cp_async_16(b_dst + i * 4096, ok ? wk + (int64_t)n * p.w_sco : w, ok ? 16u : 0u);
+            cp_async_16(b_dst + i * 4096, ok ? wk + (uint64_t)i * (32ull * p.w_sco32) : w, ok ? 16u : 0u);
           }
         }
         cp_async_commit();
@@ -514,7 +530,11 @@ int launch(const GGParams& p0, cudaStream_t stream) {
   p.tmem_cols = 32;
   while ((int)p.tmem_cols < p.n_pad) p.tmem_cols <<= 1;
   const int stage_bytes = (kABytes + p.n_pad * 128) * T::kOperands;
-  const int fixed = p.kvol * kTileM * 4 + kTileM * 4 + (p.num_chunks * 2 + 8) + (2 * kMaxStages + 1) * 8 + 128 + 1024;
+  if (p.x_row >= (int64_t)1 << 32 || p.w_sco >= (int64_t)1 << 32 || p.w_sk >= (int64_t)1 << 32 || p.cin > 65535)
+    return PV2_EUNSUPPORTED;
+  p.x_row32 = (uint32_t)p.x_row; p.w_sco32 = (uint32_t)p.w_sco; p.w_sk32 = (uint32_t)p.w_sk;
+  const int fixed = p.kvol * kTileM * 4 + kTileM * 4 + (p.num_chunks * 2 + 8) + (2 * kMaxStages + 1) * 8 + 128 +
+                    p.num_chunks * 32 + 1024;
   int stages = (220 * 1024 - fixed) / stage_bytes;
   // two resident CTAs per SM when at least two stages fit in half of the shared memory: the second CTA's setup,
   // gathers and epilogue overlap the first one's main loop (the kernel is latency-bound, not bandwidth-bound)

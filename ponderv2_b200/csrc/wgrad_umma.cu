@@ -134,7 +134,10 @@ __global__ void __launch_bounds__(kThreads, kUnits == 8 ? 2 : 1) umma_wgrad_kern
     const int piece = tid & 7;   // A: 16-byte piece (4 rows j) of a channel's 128-byte line
     const int cbase = tid >> 3;  // A: channels cbase, cbase+16, ...
     const uint32_t a_off = sw128_offset(cbase, piece);
-    const int lag = p.stages - 1;
+    // A stage is handed to the MMA warp `lag` iterations after its copies were issued and is refilled `stages`
+    // iterations later: lag = stages / 2 leaves the copies and the MMAs (issue -> commit -> barrier) about half of the
+    // ring each to complete in, instead of making every refill wait for MMAs issued one iteration earlier.
+    const int lag = p.stages >= 2 ? p.stages / 2 : 1;
     const int n_units = p.n_pad / 4;
     constexpr int kMaxUnitsPerWarp = kUnits;  // n_pad <= 256 -> 64 units / 4 warps
     const int upw = n_units / 4;          // n_pad is a multiple of 16 -> n_units is a multiple of 4
@@ -337,8 +340,8 @@ int launch_wgrad(WGParams p, cudaStream_t stream) {
     p.a_bytes = rows * 128;
   }
   const int stage_bytes = 2 * (p.a_bytes + p.n_pad * 128);
-  // + the active-stage list (added below) + 16 KB the M = 128 MMA may read past a short A tile of the last stage
-  int fixed = (2 * kMaxStages + 2) * 8 + 64 + 1024 + kMaxABytes;
+  // + the active-stage list (added below) + what the M = 128 MMA may read past a short A tile of the last stage
+  int fixed = (2 * kMaxStages + 2) * 8 + 64 + 1024 + (kMaxABytes - p.a_bytes);
   const int m_tiles = (p.cout + 127) / 128;
   // ~4 CTAs per SM in total, chunks of at least 256 rows
   int64_t chunks = (4LL * PV2_SM_COUNT + (int64_t)p.kvol * m_tiles - 1) / ((int64_t)p.kvol * m_tiles);
@@ -355,7 +358,7 @@ int launch_wgrad(WGParams p, cudaStream_t stream) {
   // CTA's gathers overlap the first one's splits and stores); otherwise one CTA with up to four stages
   static int want_ctas = -1;
   if (want_ctas < 0) { const char* e = getenv("PV2_WGRAD_CTAS"); want_ctas = e ? atoi(e) : 2; }
-  int stages = (194 * 1024 - fixed) / stage_bytes;
+  int stages = (224 * 1024 - fixed) / stage_bytes;
   if (want_ctas >= 2 && (112 * 1024 - fixed) / stage_bytes >= 2) stages = (112 * 1024 - fixed) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return PV2_EUNSUPPORTED;

@@ -372,3 +372,46 @@ def test_smooth_sampler_rejects_cpu_and_noncontiguous(cuda_lib):
     with pytest.raises(RuntimeError):
         SmoothSampler.apply(torch.rand(1, 2, 3, 3, 6, device=dev)[..., ::2], torch.rand(1, 1, 1, 4, 3, device=dev),
                             "zeros", True, False)
+
+
+# ------------------------------------------------------------------------------------------ fused BatchNorm + ReLU
+@pytest.mark.parametrize("c,with_res,relu", [(32, False, True), (96, True, True), (256, False, False), (64, True, True)])
+def test_bn_act_matches_torch(cuda_lib, c, with_res, relu):
+    """bn_act == relu(BatchNorm1d(x) + residual) in training mode: outputs, all gradients and the running buffers
+    (fp32 tolerance; statistics are accumulated in a different order than torch's Welford pass)."""
+    from torch import nn
+    from ponderv2_b200.bn_act import bn_act
+    dev = _dev()
+    torch.manual_seed(c)
+    n = 3001
+    x0 = (torch.randn(n, c, device=dev) * 2.0 + 0.7)
+    r0 = torch.randn(n, c, device=dev) if with_res else None
+    g = torch.randn(n, c, device=dev)
+    w0 = torch.rand(c, device=dev) + 0.5
+    b0 = torch.rand(c, device=dev) - 0.5
+    outs = []
+    for fused in (False, True):
+        bn = nn.BatchNorm1d(c, eps=1e-3, momentum=0.01).to(dev).train()
+        with torch.no_grad():
+            bn.weight.copy_(w0); bn.bias.copy_(b0)
+        x = x0.clone().requires_grad_(True)
+        r = r0.clone().requires_grad_(True) if with_res else None
+        if fused:
+            y = bn_act(x, bn, r, relu)
+        else:
+            y = bn(x)
+            if r is not None:
+                y = y + r
+            if relu:
+                y = torch.relu(y)
+        y.backward(g)
+        outs.append((y.detach(), x.grad, r.grad if r is not None else None, bn.weight.grad, bn.bias.grad,
+                     bn.running_mean.clone(), bn.running_var.clone(), int(bn.num_batches_tracked)))
+    ref, got = outs
+    for i, name in enumerate(["y", "dx", "dres", "dgamma", "dbeta", "running_mean", "running_var"]):
+        if ref[i] is None:
+            assert got[i] is None
+            continue
+        err = (ref[i] - got[i]).abs().max().item()
+        assert err < 2e-5 * max(1.0, ref[i].abs().max().item()), (name, err)
+    assert ref[7] == got[7] == 1
