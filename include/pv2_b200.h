@@ -109,6 +109,10 @@ int pv2_spconv_gather_gemm(const void* x, const void* w, int64_t w_stride_co, in
  * workspaces uniformly. */
 size_t pv2_spconv_workspace_bytes(int64_t n_in, int cin, int cout, int kvol, int dtype);
 
+/* Weights for the data gradient: out[ci][k][co] = w[co][flip ? K-1-k : k][ci]  (w is [cout, kvol, cin], out
+ * [cin, kvol, cout]); with flip = 1 a submanifold conv's dgrad is pv2_spconv_gather_gemm over the forward map. */
+int pv2_spconv_dgrad_weights(const void* w, void* out, int cout, int kvol, int cin, int flip, int dtype, void* stream);
+
 /* dw[co, k, ci] (+)= sum_j dy[j, co] * x[nbr[k][j], ci];  dw is float32 [Cout, K, Cin], must be
  * zeroed by the caller (accumulated with atomics across row chunks). */
 /* row_order / nbr as for pv2_spconv_gather_gemm; blk_active (optional) from pv2_rulebook_row_order. */

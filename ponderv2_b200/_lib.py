@@ -33,6 +33,7 @@ SIGNATURES = {
     "pv2_rulebook_row_order": (_int, [_vp, _i64, _int, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pv2_spconv_gather_gemm": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _i64, _int, _int, _int, _int, _vp,
                                        _sz, _vp]),
+    "pv2_spconv_dgrad_weights": (_int, [_vp, _vp, _int, _int, _int, _int, _int, _vp]),
     "pv2_spconv_workspace_bytes": (_sz, [_i64, _int, _int, _int, _int]),
     "pv2_spconv_wgrad": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _int, _int, _int, _int, _vp, _sz, _vp]),
     "pv2_wgrad_workspace_bytes": (_sz, [_i64, _i64, _int, _int]),

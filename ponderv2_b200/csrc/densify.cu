@@ -111,3 +111,44 @@ int pv2_densify_bwd(const float* dvolume, const int64_t* cell, const int32_t* co
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------
+// Weight layout for the data gradient of a sparse convolution: out[ci][k][co] = w[co][flip ? K-1-k : k][ci]
+// (the k-flip is the submanifold symmetry nbr[k][j] = i <=> nbr[K-1-k][i] = j, so dgrad reuses the forward map).
+// One 32x32 shared-memory tile transpose per (k, tile): coalesced on both sides.  Replaces a torch flip + permute + copy.
+namespace {
+template <typename T>
+__global__ void __launch_bounds__(256) dgrad_weights_kernel(const T* __restrict__ w, T* __restrict__ out, int cout, int kvol,
+                                                            int cin, int flip) {
+  __shared__ T tile[32][33];
+  const int k = blockIdx.z;
+  const int ks = flip ? kvol - 1 - k : k;
+  const int co0 = blockIdx.y * 32, ci0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int co = co0 + ty + 8 * i, ci = ci0 + tx;
+    if (co < cout && ci < cin) tile[ty + 8 * i][tx] = w[((int64_t)co * kvol + ks) * cin + ci];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int ci = ci0 + ty + 8 * i, co = co0 + tx;
+    if (ci < cin && co < cout) out[((int64_t)ci * kvol + k) * cout + co] = tile[tx][ty + 8 * i];
+  }
+}
+}  // namespace
+
+extern "C" int pv2_spconv_dgrad_weights(const void* w, void* out, int cout, int kvol, int cin, int flip, int dtype,
+                                        void* stream_) {
+  PV2_CHECK_ARG(cout > 0 && kvol > 0 && cin > 0 && kvol <= 65535 && w != nullptr && out != nullptr);
+  dim3 grid((unsigned)((cin + 31) / 32), (unsigned)((cout + 31) / 32), (unsigned)kvol);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (dtype == PV2_F32)
+    dgrad_weights_kernel<float><<<grid, 256, 0, stream>>>((const float*)w, (float*)out, cout, kvol, cin, flip);
+  else if (dtype == PV2_BF16)
+    dgrad_weights_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)w, (__nv_bfloat16*)out, cout, kvol, cin, flip);
+  else
+    return PV2_EUNSUPPORTED;
+  PV2_DONE(1);
+}

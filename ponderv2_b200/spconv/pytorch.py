@@ -241,8 +241,13 @@ class _SparseConvFunction(torch.autograd.Function):
         dy = dy.contiguous().to(xc.dtype)
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            wt = w3.flip(1) if ctx.flip else w3
-            wt = wt.permute(2, 1, 0).contiguous()  # [Cin, K, Cout]
+            cout_, kvol_, cin_ = w3.shape
+            wt = torch.empty((cin_, kvol_, cout_), dtype=w3.dtype, device=w3.device)   # [Cin, K, Cout], k-flipped for SubM
+            lib = _lib.load()
+            with torch.cuda.device(w3.device):
+                _lib.check(lib.pv2_spconv_dgrad_weights(_lib.ptr(w3.contiguous()), _lib.ptr(wt), cout_, kvol_, cin_,
+                                                        int(ctx.flip), _lib.dtype_code(w3.dtype), _lib.stream_ptr()),
+                           "pv2_spconv_dgrad_weights")
             dx = _gather_gemm(dy, wt, None, ctx.map_bwd, xc.shape[0]).to(ctx.x_dtype)[:, :ctx.cin_orig]
         if ctx.needs_input_grad[1]:
             dw = _wgrad(xc, dy, ctx.map_fwd, w3.shape[1]).reshape(ctx.weight_shape).to(ctx.weight_dtype)[..., :ctx.cin_orig]
