@@ -11,7 +11,7 @@
 
 namespace {
 
-constexpr int kRowsPerBlock = 256;
+constexpr int kRowsPerBlock = 64;    // many small blocks: the reduction passes are latency-bound at 100 k rows
 constexpr int kBnThreads = 256;
 
 // Per-block column sums of up to two quantities.  Thread t owns channel group (t % C4) and rows (t / C4) + i * RP.
@@ -36,6 +36,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_partial_kernel(const float4* __
     is = *reinterpret_cast<const float4*>(invstd + cg * 4);
   }
   if (active) {
+#pragma unroll 4
     for (int64_t r = rt; r < rows; r += RP) {
       const int64_t e = (row0 + r) * C4 + cg;
       const float4 v = __ldg(&x[e]);
@@ -68,20 +69,32 @@ __global__ void __launch_bounds__(kBnThreads) bn_partial_kernel(const float4* __
   }
 }
 
-// one thread per channel: combine the per-block partial sums in double
+// Combine the per-block partial sums in double, deterministically: block = 32 channels, warp w sums partial blocks
+// w, w + 8, ... (coalesced 128-byte reads), the eight warp totals are added in a fixed order.
 // MODE 0: mean / invstd (+ running statistics, torch semantics: momentum, unbiased running variance)
 // MODE 1: dgamma = sum dz * xhat, dbeta = sum dz
 template <int MODE>
-__global__ void bn_finalize_kernel(const float* __restrict__ partial, int nblk, int C, int64_t N, float eps, float momentum,
-                                   float* __restrict__ out_a, float* __restrict__ out_b, float* __restrict__ running_mean,
-                                   float* __restrict__ running_var) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+__global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restrict__ partial, int nblk, int C, int64_t N,
+                                                          float eps, float momentum, float* __restrict__ out_a,
+                                                          float* __restrict__ out_b, float* __restrict__ running_mean,
+                                                          float* __restrict__ running_var) {
+  __shared__ double s_a[8][32], s_b[8][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
   double sa = 0.0, sb = 0.0;
-  for (int b = 0; b < nblk; ++b) {
-    sa += (double)partial[((int64_t)b * 2) * C + c];
-    sb += (double)partial[((int64_t)b * 2 + 1) * C + c];
+  if (c < C) {
+#pragma unroll 4
+    for (int b = w; b < nblk; b += 8) {
+      sa += (double)__ldg(&partial[((int64_t)b * 2) * C + c]);
+      sb += (double)__ldg(&partial[((int64_t)b * 2 + 1) * C + c]);
+    }
   }
+  s_a[w][lane] = sa; s_b[w][lane] = sb;
+  __syncthreads();
+  if (w != 0 || c >= C) return;
+  sa = 0.0; sb = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { sa += s_a[i][lane]; sb += s_b[i][lane]; }
   if (MODE == 0) {
     const double m = sa / (double)N;
     double var = sb / (double)N - m * m;
@@ -173,7 +186,7 @@ int pv2_bn_act_fwd(const float* x, const float* res, const float* gamma, const f
   const int nblk = nblocks_for(n), C4 = c / 4;
   bn_partial_kernel<0><<<nblk, kBnThreads, 0, stream>>>((const float4*)x, nullptr, nullptr, nullptr, nullptr, n, C4, 0,
                                                          (float4*)workspace);
-  bn_finalize_kernel<0><<<(c + 127) / 128, 128, 0, stream>>>((const float*)workspace, nblk, c, n, eps, momentum, mean, invstd,
+  bn_finalize_kernel<0><<<(c + 31) / 32, 256, 0, stream>>>((const float*)workspace, nblk, c, n, eps, momentum, mean, invstd,
                                                              running_mean, running_var);
   const int64_t total4 = n * C4;
   bn_apply_fwd_kernel<<<pv2_grid_for(total4, 256), 256, 0, stream>>>((const float4*)x, (const float4*)res, mean, invstd, gamma, beta,
@@ -194,7 +207,7 @@ int pv2_bn_act_bwd(const float* x, const float* dy, const float* y, const float*
   const int nblk = nblocks_for(n), C4 = c / 4;
   bn_partial_kernel<1><<<nblk, kBnThreads, 0, stream>>>((const float4*)x, (const float4*)dy, (const float4*)y, mean, invstd, n, C4,
                                                          relu, (float4*)workspace);
-  bn_finalize_kernel<1><<<(c + 127) / 128, 128, 0, stream>>>((const float*)workspace, nblk, c, n, 0.f, 0.f, dgamma, dbeta, nullptr,
+  bn_finalize_kernel<1><<<(c + 31) / 32, 256, 0, stream>>>((const float*)workspace, nblk, c, n, 0.f, 0.f, dgamma, dbeta, nullptr,
                                                              nullptr);
   const int64_t total4 = n * C4;
   bn_apply_bwd_kernel<<<pv2_grid_for(total4, 256), 256, 0, stream>>>((const float4*)x, (const float4*)dy, (const float4*)y, mean,

@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(256) field_post_fwd_kernel(const float* __rest
 //   d f_r = inbar[3:67]  -> dF[:, cs:2cs];  d geo = inbar[67:131], d sdf = g_sdf  -> doutbar [P, 68]
 //   ubar  = sum_i (dw_i . gbar) V_i[0:cs]  -> [P,64]  (second-order term: d grad / d u)
 //   dMr  += zbar (x) in,  dcr += zbar     (block partial sums, then atomics)
-__global__ void __launch_bounds__(256) field_post_bwd_kernel(
+__global__ void __launch_bounds__(256, 2) field_post_bwd_kernel(
     const float* __restrict__ vol, const float* __restrict__ pts, const float* __restrict__ dirs, int samples_per_ray,
     const float* __restrict__ f_r, const float* __restrict__ out_geo, int64_t geo_row, const float* __restrict__ grad,
     const float* __restrict__ rgb, const float* __restrict__ Mr, const float* __restrict__ g_rgb,

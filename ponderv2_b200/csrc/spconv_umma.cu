@@ -31,9 +31,7 @@ namespace {
 using namespace pv2;
 
 constexpr int kTileM = 128;
-constexpr int kProducerWarps = 8;
-constexpr int kProducerThreads = kProducerWarps * 32;
-constexpr int kThreads = kProducerThreads + 32;
+constexpr int kMaxProducerWarps = 12;   // fp32: kGroups (2 or 3) groups of 4 producer warps; bf16: 8 warps
 constexpr int kABytes = kTileM * 128;  // one operand tile: 128 rows x 128 B
 constexpr int kMaxStages = 6;
 
@@ -105,9 +103,13 @@ __device__ __forceinline__ void split_store(uint32_t addr, uint32_t lo_delta, co
 
 // kPre (fp32 only): x is stored split-precision (value = x[..] + x[.. + x_lo_off]); a template parameter because a
 // predicated-off FADD on a just-loaded register still waits for the load, which serialises the gather.
-template <bool kSplit, bool kPre>
-__global__ void __launch_bounds__(kThreads) umma_gather_gemm_kernel(const GGParams p) {
+// kGroups (fp32): groups of four producer warps that alternate chunks (group g takes chunks g, g + kGroups, ...).
+template <bool kSplit, bool kPre, int kGroups>
+__global__ void __launch_bounds__(kGroups * 128 + 32) umma_gather_gemm_kernel(const GGParams p) {
   using T = ModeTraits<kSplit>;
+  constexpr int kProducerWarps = kGroups * 4;
+  constexpr int kProducerThreads = kProducerWarps * 32;
+  constexpr int kThreads = kProducerThreads + 32;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // dynamic smem is only guaranteed 16 B aligned: round up to 1024 (the launch reserves the slack)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -130,8 +132,8 @@ __global__ void __launch_bounds__(kThreads) umma_gather_gemm_kernel(const GGPara
   uint64_t* tmem_full_bar = bars + 2 * kMaxStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 1);
   uint32_t* kmask_s = tmem_slot + 1;                       // [4]: one bit per kernel offset (K <= 128)
-  int* wcount_s = reinterpret_cast<int*>(tmem_slot + 5);  // [kProducerWarps + 1]
-  uint32_t* kc_s = reinterpret_cast<uint32_t*>(wcount_s + kProducerWarps + 1);   // [num_chunks][8]: (k << 16 | ci) per 16-byte piece
+  int* wcount_s = reinterpret_cast<int*>(tmem_slot + 5);  // [kMaxProducerWarps + 1]
+  uint32_t* kc_s = reinterpret_cast<uint32_t*>(wcount_s + kMaxProducerWarps + 1);   // [num_chunks][8]: (k << 16 | ci) per 16-byte piece
 
   // ---- setup ---------------------------------------------------------------------------------------------
   if (tid < kTileM) {
@@ -142,7 +144,7 @@ __global__ void __launch_bounds__(kThreads) umma_gather_gemm_kernel(const GGPara
   }
   if (tid == 0) {
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(smem_u32(&full_bar[s]), kSplit ? kProducerThreads / 2 : kProducerThreads);
+      mbar_init(smem_u32(&full_bar[s]), kSplit ? 128 : kProducerThreads);
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
     mbar_init(smem_u32(tmem_full_bar), 1);
@@ -258,7 +260,7 @@ __global__ void __launch_bounds__(kThreads) umma_gather_gemm_kernel(const GGPara
       const float* wrow0 = w + (uint64_t)rbase * p.w_sco32;   // loop-invariant: weight row rbase
       const uint64_t wstep = 16ull * p.w_sco32;                // rows rbase + 16 i
       const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int it = grp; it < n_active; it += 2) {
+      for (int it = grp; it < n_active; it += kGroups) {
         const int c = chunk_at(it);
         const int s = it % p.stages;
         const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
@@ -380,7 +382,7 @@ __global__ void __launch_bounds__(kThreads) umma_gather_gemm_kernel(const GGPara
     const int32_t j32 = row_s[lane_grp * 32 + lane];
     const int64_t j = j32;
     const bool row_ok = j32 >= 0;
-    for (int col0 = (warp >> 2) * 16; col0 < p.n_pad; col0 += 32) {
+    for (int col0 = (warp >> 2) * 16; col0 < p.n_pad; col0 += 16 * kGroups) {
       uint32_t v[16];
       if (n_active > 0) {
         tmem_ld_x16(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)col0, v);
@@ -521,7 +523,7 @@ __global__ void __launch_bounds__(kThreads) umma_gather_gemm_kernel(const GGPara
   }
 }
 
-template <bool kSplit, bool kPre>
+template <bool kSplit, bool kPre, int kGroups>
 int launch(const GGParams& p0, cudaStream_t stream) {
   using T = ModeTraits<kSplit>;
   GGParams p = p0;
@@ -534,7 +536,7 @@ int launch(const GGParams& p0, cudaStream_t stream) {
     return PV2_EUNSUPPORTED;
   p.x_row32 = (uint32_t)p.x_row; p.w_sco32 = (uint32_t)p.w_sco; p.w_sk32 = (uint32_t)p.w_sk;
   const int fixed = p.kvol * kTileM * 4 + kTileM * 4 + (p.num_chunks * 2 + 8) + (2 * kMaxStages + 1) * 8 + 128 +
-                    p.num_chunks * 32 + 1024;
+                    p.num_chunks * 32 + 1024 + 64;
   int stages = (220 * 1024 - fixed) / stage_bytes;
   // two resident CTAs per SM when at least two stages fit in half of the shared memory: the second CTA's setup,
   // gathers and epilogue overlap the first one's main loop (the kernel is latency-bound, not bandwidth-bound)
@@ -547,7 +549,7 @@ int launch(const GGParams& p0, cudaStream_t stream) {
   const size_t smem = (size_t)stages * stage_bytes + fixed;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(umma_gather_gemm_kernel<kSplit, kPre>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(umma_gather_gemm_kernel<kSplit, kPre, kGroups>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          227 * 1024);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
@@ -567,11 +569,25 @@ int launch(const GGParams& p0, cudaStream_t stream) {
     ++launches;
   }
   dim3 grid(tiles, (unsigned)ksplit);
-  umma_gather_gemm_kernel<kSplit, kPre><<<grid, kThreads, smem, stream>>>(p);
+  umma_gather_gemm_kernel<kSplit, kPre, kGroups><<<grid, kGroups * 128 + 32, smem, stream>>>(p);
   PV2_DONE(launches);
 }
 
 }  // namespace
+
+// Producer groups of the fp32 kernel.  Narrow layers (two stages fit in half of the shared memory) run two resident
+// CTAs of 2 groups each; wide layers are limited to one CTA per SM by shared memory and get a third group instead.
+// PV2_GG_GROUPS = 2 | 3 forces one setting (development switch).
+static int fp32_groups(int cout, int kvol, int cin) {
+  static int forced = -1;
+  if (forced < 0) { const char* e = getenv("PV2_GG_GROUPS"); forced = e ? atoi(e) : 0; }
+  if (forced == 2 || forced == 3) return forced;
+  const int n_pad = (cout + 15) / 16 * 16;
+  const int num_chunks = (kvol * cin + 31) / 32;
+  const int stage_bytes = (kABytes + n_pad * 128) * 2;
+  const int fixed = kvol * kTileM * 4 + kTileM * 4 + (num_chunks * 2 + 8) + (2 * kMaxStages + 1) * 8 + 128 + num_chunks * 32 + 1024 + 64;
+  return (112 * 1024 - fixed) / stage_bytes >= 2 ? 2 : 3;
+}
 
 extern "C" {
 
@@ -610,7 +626,9 @@ int pv2_spconv_gather_gemm_umma(const void* x, const void* w, int64_t w_sco, int
     q.w = (const char*)w + (size_t)co0 * w_sco * eb;
     q.bias = bias ? bias + co0 : nullptr;
     q.y = (char*)y + (size_t)co0 * eb;
-    const int rc = dtype == PV2_BF16 ? launch<false, false>(q, stream) : launch<true, false>(q, stream);
+    const int rc = dtype == PV2_BF16 ? launch<false, false, 2>(q, stream)
+                                     : (fp32_groups(q.cout, kvol, cin) == 3 ? launch<true, false, 3>(q, stream)
+                                                                            : launch<true, false, 2>(q, stream));
     if (rc != 0) return rc;
   }
   return 0;
@@ -645,7 +663,9 @@ int pv2_linear(const float* x, int64_t x_row, int64_t x_lo_off, int x_presplit, 
   p.bias = bias; p.nbr = nullptr; p.order = nullptr; p.y = y; p.n_out = rows; p.cin = cin; p.cout = cout; p.kvol = 1;
   p.y_row = y_row; p.y_lo_off = y_lo_off; p.y_split = y_split; p.act = act;
   p.y2 = y2; p.y2_row = y2_row; p.y2_lo_off = y2_lo_off;
-  return x_presplit ? launch<true, true>(p, (cudaStream_t)stream_) : launch<true, false>(p, (cudaStream_t)stream_);
+  if (x_presplit) return launch<true, true, 2>(p, (cudaStream_t)stream_);
+  return fp32_groups(cout, 1, cin) == 3 ? launch<true, false, 3>(p, (cudaStream_t)stream_)
+                                        : launch<true, false, 2>(p, (cudaStream_t)stream_);
 }
 
 }  // extern "C"

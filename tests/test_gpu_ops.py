@@ -415,3 +415,51 @@ def test_bn_act_matches_torch(cuda_lib, c, with_res, relu):
         err = (ref[i] - got[i]).abs().max().item()
         assert err < 2e-5 * max(1.0, ref[i].abs().max().item()), (name, err)
     assert ref[7] == got[7] == 1
+
+
+# ------------------------------------------------------------------------------------------ BASELINE-size properties
+def test_full_size_rulebook_and_conv_properties(cuda_lib):
+    """BASELINE configs[1] size (100 k voxels): rulebooks bit-exact against the oracle, the submanifold symmetry
+    nbr[k][j] = i <=> nbr[K-1-k][i] = j, exactly one pair per fine voxel in the strided rulebook, and size-independent
+    properties of the convolution kernels: linearity and independence of the tile order."""
+    import ponderv2_b200.spconv.pytorch as spconv
+    dev = _dev()
+    n = 100_000
+    ind, shape = _indoor_indices(n, 2000)
+    ind_t = torch.from_numpy(ind).to(dev)
+    rb = spconv.build_subm_rulebook(ind_t, shape, 3)
+    nbr = rb.nbr.cpu().numpy()
+    assert np.array_equal(nbr, so.subm_rulebook(ind, shape, 3))                       # bit-exact at full size
+    assert rb.num_pairs == int((nbr >= 0).sum())
+    assert np.array_equal(nbr[13], np.arange(n, dtype=np.int32))                      # centre offset = identity
+    for k in (0, 5, 12):                                                              # symmetry
+        j = np.nonzero(nbr[k] >= 0)[0]
+        assert np.array_equal(nbr[26 - k][nbr[k][j]], j.astype(np.int32))
+    d = spconv.build_down_rulebook(ind_t, shape)
+    oc, in2out, koff, _ = so.down_rulebook(ind, shape)
+    assert d.out_indices.shape[0] == oc.shape[0]
+    up = d.nbr_up.cpu().numpy()
+    assert ((up >= 0).sum(0) == 1).all()                                              # one pair per fine voxel
+    got_c, got_map, _ = so.canonical_down(d.out_indices.cpu().numpy(), d.in2out.cpu().numpy(), d.out_shape)
+    ref_c, ref_map, _ = so.canonical_down(oc, in2out, d.out_shape)
+    assert np.array_equal(got_c, ref_c) and np.array_equal(got_map, ref_map)
+
+    torch.manual_seed(3)
+    cin, cout = 32, 64
+    x1, x2 = torch.randn(n, cin, device=dev), torch.randn(n, cin, device=dev)
+    w3 = torch.randn(cout, 27, cin, device=dev) * 0.05
+    f = lambda x, tm: spconv._gather_gemm(x, w3, None, tm, n)
+    y1, y2, y12 = f(x1, rb.tmap), f(x2, rb.tmap), f(2.0 * x1 - 3.0 * x2, rb.tmap)
+    scale = y12.abs().max().item()
+    assert (y12 - (2.0 * y1 - 3.0 * y2)).abs().max().item() < 2e-5 * scale            # linearity
+    y_nat = f(x1, spconv.TileMap(rb.nbr))                                             # natural row order, no skipping
+    assert (y_nat - y1).abs().max().item() < 2e-5 * y1.abs().max().item()             # tile order changes nothing
+    dy = torch.randn(n, cout, device=dev)
+    dw_a = spconv._wgrad(x1, dy, rb.tmap, 27)
+    dw_b = spconv._wgrad(x1, dy, spconv.TileMap(rb.nbr), 27)
+    assert (dw_a - dw_b).abs().max().item() < 2e-5 * dw_b.abs().max().item()
+    # adjointness of fwd and dgrad: <conv(x), dy> == <x, dgrad(dy)>
+    wt = w3.flip(1).permute(2, 1, 0).contiguous()
+    dx = spconv._gather_gemm(dy, wt, None, rb.tmap, n)
+    lhs, rhs = (y1.double() * dy.double()).sum().item(), (x1.double() * dx.double()).sum().item()
+    assert abs(lhs - rhs) < 1e-5 * (y1.double().abs() * dy.double().abs()).sum().item()
