@@ -10,7 +10,7 @@ tail -15 $out/${tag}_pytest.log
 if [ "${SKIP_MICRO:-0}" != "1" ]; then
   timeout 600 python tools/spconv_microbench.py --levels --out $out/${tag}_micro_levels.json 2>&1 | tee $out/${tag}_micro_levels.txt
   if [ "${MICRO_AB:-0}" = "1" ]; then
-    PV2_GG_CTAS=1 PV2_WGRAD_CTAS=1 timeout 600 python tools/spconv_microbench.py --levels 2>&1 | tee $out/${tag}_micro_levels_1cta.txt
+    env ${MICRO_AB_ENV:-PV2_GG_GROUPS=2} timeout 600 python tools/spconv_microbench.py --levels 2>&1 | tee $out/${tag}_micro_levels_ab.txt
   fi
   if [ "${MICRO_NOORDER:-0}" = "1" ]; then
     PV2_ROW_ORDER=0 timeout 600 python tools/spconv_microbench.py --levels 2>&1 | tee $out/${tag}_micro_levels_noorder.txt
