@@ -577,16 +577,19 @@ int launch(const GGParams& p0, cudaStream_t stream) {
 
 // Producer groups of the fp32 kernel.  Narrow layers (two stages fit in half of the shared memory) run two resident
 // CTAs of 2 groups each; wide layers are limited to one CTA per SM by shared memory and get a third group instead.
-// PV2_GG_GROUPS = 2 | 3 forces one setting (development switch).
+// PV2_GG_GROUPS = 2 forces two groups everywhere (development switch).
 static int fp32_groups(int cout, int kvol, int cin) {
   static int forced = -1;
   if (forced < 0) { const char* e = getenv("PV2_GG_GROUPS"); forced = e ? atoi(e) : 0; }
-  if (forced == 2 || forced == 3) return forced;
+  if (forced == 2) return 2;
   const int n_pad = (cout + 15) / 16 * 16;
   const int num_chunks = (kvol * cin + 31) / 32;
   const int stage_bytes = (kABytes + n_pad * 128) * 2;
   const int fixed = kvol * kTileM * 4 + kTileM * 4 + (num_chunks * 2 + 8) + (2 * kMaxStages + 1) * 8 + 128 + num_chunks * 32 + 1024 + 64;
-  return (112 * 1024 - fixed) / stage_bytes >= 2 ? 2 : 3;
+  if ((112 * 1024 - fixed) / stage_bytes >= 2) return 2;
+  // A group may only wait one phase ahead on a stage's mbarrier (parity waits alias every second phase): with more
+  // groups than stages a fast group would see the completion it needs as already past.  Hence groups <= stages.
+  return (220 * 1024 - fixed) / stage_bytes >= 3 ? 3 : 2;
 }
 
 extern "C" {
