@@ -103,6 +103,10 @@ __device__ __forceinline__ void split_store(uint32_t addr, uint32_t lo_delta, co
 
 // kPre (fp32 only): x is stored split-precision (value = x[..] + x[.. + x_lo_off]); a template parameter because a
 // predicated-off FADD on a just-loaded register still waits for the load, which serialises the gather.
+// 16 zero bytes in global memory: missing neighbours / padding rows load from here instead of predicating the load and
+// zero-filling registers (fewer instructions in the gather prologue)
+__device__ float4 g_zero_page[2];
+
 // kGroups (fp32): groups of four producer warps that alternate chunks (group g takes chunks g, g + kGroups, ...).
 template <bool kSplit, bool kPre, int kGroups>
 __global__ void __launch_bounds__(kGroups * 128 + 32) umma_gather_gemm_kernel(const GGParams p) {
@@ -117,7 +121,9 @@ __global__ void __launch_bounds__(kGroups * 128 + 32) umma_gather_gemm_kernel(co
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
-  const int64_t row0 = (int64_t)blockIdx.x * kTileM;
+  // Tiles are taken in reverse: in mask-sorted order the rows with the most neighbours (highest masks, most chunks) come
+  // last, and the longest tiles should start first so that the last wave is short ones.
+  const int64_t row0 = (int64_t)(gridDim.x - 1 - blockIdx.x) * kTileM;
 
   const int b_bytes = p.n_pad * 128;
   const int stage_bytes = (kABytes + b_bytes) * T::kOperands;
@@ -238,7 +244,7 @@ __global__ void __launch_bounds__(kGroups * 128 + 32) umma_gather_gemm_kernel(co
     if (n_active > per) n_active = per;
     if (n_active < 0) n_active = 0;
   }
-  const int rot = (n_total > 1) ? (int)((blockIdx.x * 11u) % (unsigned)n_total) : 0;
+  const int rot = (n_total > 1) ? (int)(((unsigned)(row0 >> 7) * 11u) % (unsigned)n_total) : 0;
   auto chunk_at = [&](int it) -> int {
     int q = first + it + rot;
     if (q >= n_total) q -= n_total;
@@ -260,6 +266,7 @@ __global__ void __launch_bounds__(kGroups * 128 + 32) umma_gather_gemm_kernel(co
       const float* wrow0 = w + (uint64_t)rbase * p.w_sco32;   // loop-invariant: weight row rbase
       const uint64_t wstep = 16ull * p.w_sco32;                // rows rbase + 16 i
       const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float* zpage = reinterpret_cast<const float*>(g_zero_page);
       for (int it = grp; it < n_active; it += kGroups) {
         const int c = chunk_at(it);
         const int s = it % p.stages;
@@ -274,11 +281,8 @@ __global__ void __launch_bounds__(kGroups * 128 + 32) umma_gather_gemm_kernel(co
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int32_t src = kvalid ? idx_k[rbase + 16 * i] : -1;
-          va[i] = zero4;
-          if (src >= 0) {
-            const float* g = x + ((uint64_t)(uint32_t)src * p.x_row32 + ci);
-            va[i] = __ldg(reinterpret_cast<const float4*>(g));
-          }
+          const float* g = (src >= 0) ? x + ((uint64_t)(uint32_t)src * p.x_row32 + ci) : zpage;
+          va[i] = __ldg(reinterpret_cast<const float4*>(g));
         }
         if constexpr (kPre) {   // split-precision input: add the lo halves (second batch of loads, then the adds)
           float4 vl[8];
@@ -296,8 +300,8 @@ __global__ void __launch_bounds__(kGroups * 128 + 32) umma_gather_gemm_kernel(co
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int n = rbase + 16 * i;
-          vb[i] = zero4;
-          if (kvalid && i < nb && n < p.cout) vb[i] = __ldg(reinterpret_cast<const float4*>(wk + (uint64_t)i * wstep));
+          const float* g = (kvalid && i < nb && n < p.cout) ? wk + (uint64_t)i * wstep : zpage;
+          vb[i] = __ldg(reinterpret_cast<const float4*>(g));
         }
         mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
         const uint32_t a_dst = smem_u32(stage_base + (size_t)s * stage_bytes) + tile_off;
@@ -311,8 +315,8 @@ __global__ void __launch_bounds__(kGroups * 128 + 32) umma_gather_gemm_kernel(co
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int n = rbase + 16 * (i + 8);
-            vb[i] = zero4;
-            if (kvalid && i + 8 < nb && n < p.cout) vb[i] = __ldg(reinterpret_cast<const float4*>(wk + (uint64_t)(i + 8) * wstep));
+            const float* g = (kvalid && i + 8 < nb && n < p.cout) ? wk + (uint64_t)(i + 8) * wstep : zpage;
+            vb[i] = __ldg(reinterpret_cast<const float4*>(g));
           }
 #pragma unroll
           for (int i = 0; i < 8; ++i)

@@ -457,7 +457,8 @@ def test_full_size_rulebook_and_conv_properties(cuda_lib):
     dy = torch.randn(n, cout, device=dev)
     dw_a = spconv._wgrad(x1, dy, rb.tmap, 27)
     dw_b = spconv._wgrad(x1, dy, spconv.TileMap(rb.nbr), 27)
-    assert (dw_a - dw_b).abs().max().item() < 2e-5 * dw_b.abs().max().item()
+    # fp32 accumulation over 1e5 rows in two different orders (plus atomics across row chunks): 1e-4 of the magnitude
+    assert (dw_a - dw_b).abs().max().item() < 1e-4 * dw_b.abs().max().item()
     # adjointness of fwd and dgrad: <conv(x), dy> == <x, dgrad(dy)>
     wt = w3.flip(1).permute(2, 1, 0).contiguous()
     dx = spconv._gather_gemm(dy, wt, None, rb.tmap, n)
