@@ -59,6 +59,7 @@ struct GGParams {
                      // 2..4: backward epilogues reading y2 / the old y (see the epilogue)
   void* y2;
   int64_t y2_row, y2_lo_off;
+  int ablate;        // development only (PV2_GG_ABLATE): 1 skip the global loads, 2 skip split + st.shared, 4 skip the MMAs
   int ksplit;        // > 1: gridDim.y CTAs share one row tile, each reduces a slice of the contraction and adds its
                      // partial result into the (pre-zeroed) output with red.global.add (small deep U-Net levels)
 };
@@ -281,7 +282,7 @@ __global__ void __launch_bounds__(kGroups * 128 + 32) umma_gather_gemm_kernel(co
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int32_t src = kvalid ? idx_k[rbase + 16 * i] : -1;
-          const float* g = (src >= 0) ? x + ((uint64_t)(uint32_t)src * p.x_row32 + ci) : zpage;
+          const float* g = (src >= 0 && !(p.ablate & 1)) ? x + ((uint64_t)(uint32_t)src * p.x_row32 + ci) : zpage;
           va[i] = __ldg(reinterpret_cast<const float4*>(g));
         }
         if constexpr (kPre) {   // split-precision input: add the lo halves (second batch of loads, then the adds)
@@ -300,17 +301,21 @@ __global__ void __launch_bounds__(kGroups * 128 + 32) umma_gather_gemm_kernel(co
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int n = rbase + 16 * i;
-          const float* g = (kvalid && i < nb && n < p.cout) ? wk + (uint64_t)i * wstep : zpage;
+          const float* g = (kvalid && i < nb && n < p.cout && !(p.ablate & 1)) ? wk + (uint64_t)i * wstep : zpage;
           vb[i] = __ldg(reinterpret_cast<const float4*>(g));
         }
         mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
         const uint32_t a_dst = smem_u32(stage_base + (size_t)s * stage_bytes) + tile_off;
         const uint32_t b_dst = a_dst + 2 * kABytes;
+        if (!(p.ablate & 2)) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) split_store(a_dst + i * 2048, kABytes, va[i]);
+          for (int i = 0; i < 8; ++i) split_store(a_dst + i * 2048, kABytes, va[i]);
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          if (i < nb) split_store(b_dst + i * 2048, (uint32_t)b_bytes, vb[i]);
+          for (int i = 0; i < 8; ++i)
+            if (i < nb) split_store(b_dst + i * 2048, (uint32_t)b_bytes, vb[i]);
+        } else if (va[0].x == 123.456f && vb[0].x == 654.321f) {
+          st_shared_v4(a_dst, va[1]);   // keep the loads alive
+        }
         if (nb > 8) {  // wide layers (Cout > 128): second half of the weight rows
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -508,6 +513,7 @@ __global__ void __launch_bounds__(kGroups * 128 + 32) umma_gather_gemm_kernel(co
           const uint64_t dbl = dbh + (uint64_t)(b_bytes >> 4);
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
+            if (p.ablate & 4) break;
             umma_tf32(tmem_base, dal + 2 * ks, dbh + 2 * ks, idesc, (it | ks) != 0 ? 1u : 0u);
             umma_tf32(tmem_base, da + 2 * ks, dbl + 2 * ks, idesc, 1u);
             umma_tf32(tmem_base, da + 2 * ks, dbh + 2 * ks, idesc, 1u);
@@ -566,6 +572,11 @@ int launch(const GGParams& p0, cudaStream_t stream) {
     if (ksplit < 1) ksplit = 1;
   }
   p.ksplit = ksplit;
+  {
+    static int abl = -1;
+    if (abl < 0) { const char* e = getenv("PV2_GG_ABLATE"); abl = e ? atoi(e) : 0; }
+    p.ablate = abl;
+  }
   int launches = 1;
   if (ksplit > 1) {
     // only this launch's columns: a caller may be filling other column slices of the same rows (Cout > 256)
