@@ -104,6 +104,63 @@ __device__ __forceinline__ void split_store(uint32_t addr, uint32_t lo_delta, co
 
 // kPre (fp32 only): x is stored split-precision (value = x[..] + x[.. + x_lo_off]); a template parameter because a
 // predicated-off FADD on a just-loaded register still waits for the load, which serialises the gather.
+// fp32 output of one row's 16 accumulator columns [col0, col0 + 16): fused activation / backward epilogues, then plain or
+// split-precision stores.  (bias already added)
+__device__ __forceinline__ void fp32_row_epilogue(const GGParams& p, float (&f)[16], int64_t j, int col0) {
+  float g2[16];
+  if (p.act == 1) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float t = 100.f * f[i];
+      g2[i] = 1.f / (1.f + __expf(-t));
+      f[i] = (t > 20.f) ? f[i] : log1pf(expf(t)) * 0.01f;
+    }
+  }
+  const bool vec = (col0 + 16 <= p.cout) && ((p.cout & 3) == 0);
+  if (p.act >= 2) {
+    // backward-pass epilogues of the SDF decoder (y2 is an INPUT here, plain fp32, row stride y2_row):
+    //   2: y = v * 100 s (1 - s)       (through the softplus derivative s = sigmoid(100 h))
+    //   3: y = y_old + v * s           4: y = y_old + v
+    const float* ar = reinterpret_cast<const float*>(p.y2) + j * p.y2_row + col0;
+    const float* yo = reinterpret_cast<const float*>(p.y) + j * p.y_row + col0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      if (col0 + i < p.cout) {
+        if (p.act == 2) { const float sg = __ldg(ar + i); f[i] *= 100.f * sg * (1.f - sg); }
+        else if (p.act == 3) f[i] = yo[i] + f[i] * __ldg(ar + i);
+        else f[i] += yo[i];
+      }
+    }
+  }
+  auto store = [&](float* base, int64_t row_stride, int64_t lo_off, const float (&val)[16], bool split) {
+    float* yr = base + j * row_stride + col0;
+    if (!split) {
+      if (vec) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<float4*>(yr + 4 * q) = make_float4(val[4 * q], val[4 * q + 1], val[4 * q + 2], val[4 * q + 3]);
+      } else {
+        for (int i = 0; i < 16 && col0 + i < p.cout; ++i) yr[i] = val[i];
+      }
+    } else {
+      float hi[16], lo[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) split_tf32(val[i], hi[i], lo[i]);
+      if (vec) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          *reinterpret_cast<float4*>(yr + 4 * q) = make_float4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+          *reinterpret_cast<float4*>(yr + lo_off + 4 * q) = make_float4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+        }
+      } else {
+        for (int i = 0; i < 16 && col0 + i < p.cout; ++i) { yr[i] = hi[i]; yr[lo_off + i] = lo[i]; }
+      }
+    }
+  };
+  store(reinterpret_cast<float*>(p.y), p.y_row, p.y_lo_off, f, p.y_split != 0);
+  if (p.act == 1 && p.y2 != nullptr) store(reinterpret_cast<float*>(p.y2), p.y2_row, p.y2_lo_off, g2, p.y_split != 0);
+}
+
 // 16 zero bytes in global memory: missing neighbours / padding rows load from here instead of predicating the load and
 // zero-filling registers (fewer instructions in the gather prologue)
 __device__ float4 g_zero_page[2];
@@ -408,32 +465,8 @@ __global__ void __launch_bounds__(kGroups * 128 + 32) umma_gather_gemm_kernel(co
         f[i] = __uint_as_float(v[i]) + ((p.bias != nullptr && co < p.cout && blockIdx.y == 0) ? __ldg(&p.bias[co]) : 0.f);
       }
       if constexpr (kSplit) {
-        float g2[16];
-        if (p.act == 1) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float t = 100.f * f[i];
-            g2[i] = 1.f / (1.f + __expf(-t));
-            f[i] = (t > 20.f) ? f[i] : log1pf(expf(t)) * 0.01f;
-          }
-        }
-        const bool vec = (col0 + 16 <= p.cout) && ((p.cout & 3) == 0);
-        if (p.act >= 2) {
-          // backward-pass epilogues of the SDF decoder (y2 is an INPUT here, plain fp32, row stride y2_row):
-          //   2: y = v * 100 s (1 - s)       (through the softplus derivative s = sigmoid(100 h))
-          //   3: y = y_old + v * s           4: y = y_old + v
-          const float* ar = reinterpret_cast<const float*>(p.y2) + j * p.y2_row + col0;
-          const float* yo = reinterpret_cast<const float*>(p.y) + j * p.y_row + col0;
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            if (col0 + i < p.cout) {
-              if (p.act == 2) { const float sg = __ldg(ar + i); f[i] *= 100.f * sg * (1.f - sg); }
-              else if (p.act == 3) f[i] = yo[i] + f[i] * __ldg(ar + i);
-              else f[i] += yo[i];
-            }
-          }
-        }
-        if (p.ksplit > 1) {
+        if (p.ksplit > 1) {   // split-K partial sums (act == 0 on this path): vector reductions into the pre-zeroed rows
+          const bool vec = (col0 + 16 <= p.cout) && ((p.cout & 3) == 0);
           float* yr = reinterpret_cast<float*>(p.y) + j * p.y_row + col0;
           if (n_active > 0) {
             if (vec) {
@@ -449,33 +482,7 @@ __global__ void __launch_bounds__(kGroups * 128 + 32) umma_gather_gemm_kernel(co
           }
           continue;
         }
-        auto store = [&](float* base, int64_t row_stride, int64_t lo_off, const float (&val)[16], bool split) {
-          float* yr = base + j * row_stride + col0;
-          if (!split) {
-            if (vec) {
-#pragma unroll
-              for (int q = 0; q < 4; ++q)
-                *reinterpret_cast<float4*>(yr + 4 * q) = make_float4(val[4 * q], val[4 * q + 1], val[4 * q + 2], val[4 * q + 3]);
-            } else {
-              for (int i = 0; i < 16 && col0 + i < p.cout; ++i) yr[i] = val[i];
-            }
-          } else {
-            float hi[16], lo[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) split_tf32(val[i], hi[i], lo[i]);
-            if (vec) {
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                *reinterpret_cast<float4*>(yr + 4 * q) = make_float4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
-                *reinterpret_cast<float4*>(yr + lo_off + 4 * q) = make_float4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
-              }
-            } else {
-              for (int i = 0; i < 16 && col0 + i < p.cout; ++i) { yr[i] = hi[i]; yr[lo_off + i] = lo[i]; }
-            }
-          }
-        };
-        store(reinterpret_cast<float*>(p.y), p.y_row, p.y_lo_off, f, p.y_split != 0);
-        if (p.act == 1 && p.y2 != nullptr) store(reinterpret_cast<float*>(p.y2), p.y2_row, p.y2_lo_off, g2, p.y_split != 0);
+        fp32_row_epilogue(p, f, j, col0);
       } else {
         __nv_bfloat16* yr = reinterpret_cast<__nv_bfloat16*>(p.y) + j * p.y_row + col0;
         if (col0 + 16 <= p.cout && (p.cout & 7) == 0) {
@@ -531,6 +538,344 @@ __global__ void __launch_bounds__(kGroups * 128 + 32) umma_gather_gemm_kernel(co
     tc_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
   }
+}
+
+// ===============================================================================================================
+// Persistent variant (fp32, one CTA per SM looping over its tiles).  Measured on B200 with everything but the skeleton
+// switched off (profiles/r1j_gather_gemm_ablation.txt), the one-tile-per-CTA kernel above still spends half of its time:
+// per tile the index fetch, mask compaction, pipeline fill, accumulator drain and CTA turnover are serialised and nothing
+// else runs on the SM meanwhile.  Here the roles are decoupled and pipelined ACROSS tiles:
+//   * 4 epilogue warps prepare the metadata (rows, neighbour indices, active-chunk list) of tile i + 1 into the second
+//     metadata buffer while tile i is in the main loop, then drain tile i's accumulator;
+//   * producer groups and the MMA warp run the chunks of consecutive tiles back to back over one smem stage ring
+//     (a global chunk counter continues the ring and the group alternation across tiles);
+//   * two TMEM accumulators alternate, so the drain of tile i overlaps the MMAs of tile i + 1.
+constexpr int kPersistGroups = 2;
+constexpr int kPersistProducerWarps = kPersistGroups * 4;
+constexpr int kPersistThreads = (kPersistProducerWarps + 1 + 4) * 32;   // producers | MMA warp | 4 epilogue warps
+
+struct PersistLayout {
+  int meta_bytes;   // one metadata buffer: idx[kvol][128] | row[128] | active[num_chunks] | n_active
+  int fixed;        // everything except the stage ring
+};
+__host__ __device__ inline PersistLayout persist_layout(int kvol, int num_chunks) {
+  PersistLayout L;
+  L.meta_bytes = (kvol * kTileM * 4 + kTileM * 4 + num_chunks * 2 + 16 + 15) / 16 * 16;
+  L.fixed = 2 * L.meta_bytes + num_chunks * 32 /*kc table*/ + 32 * 8 /*barriers*/ + 64 + 1024 /*alignment*/;
+  return L;
+}
+
+__device__ __forceinline__ void bar_sync_named(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__global__ void __launch_bounds__(kPersistThreads) umma_gather_gemm_persistent_kernel(const GGParams p, int num_tiles) {
+  using T = ModeTraits<true>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b_bytes = p.n_pad * 128;
+  const int stage_bytes = (kABytes + b_bytes) * 2;
+  const PersistLayout L = persist_layout(p.kvol, p.num_chunks);
+  uint8_t* stage_base = smem;
+  uint8_t* meta_base = smem + (size_t)p.stages * stage_bytes;
+  uint32_t* kc_s = reinterpret_cast<uint32_t*>(meta_base + 2 * L.meta_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(kc_s + p.num_chunks * 8);
+  uint64_t* full_bar = bars;                        // [kMaxStages]  128 arrivals (the producing group)
+  uint64_t* empty_bar = bars + kMaxStages;          // [kMaxStages]  tcgen05.commit
+  uint64_t* meta_full = bars + 2 * kMaxStages;      // [2]           1 arrival (epilogue group leader)
+  uint64_t* meta_empty = meta_full + 2;             // [2]           producer warps + MMA warp
+  uint64_t* tmem_full = meta_empty + 2;             // [2]           tcgen05.commit / plain arrive for empty tiles
+  uint64_t* tmem_empty = tmem_full + 2;             // [2]           4 epilogue warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint32_t* scratch = tmem_slot + 1;                // [16] epilogue-group scratch (kmask[4], warp counts[4], total)
+
+  auto meta_idx = [&](int b) { return reinterpret_cast<int32_t*>(meta_base + (size_t)b * L.meta_bytes); };
+  auto meta_row = [&](int b) { return meta_idx(b) + p.kvol * kTileM; };
+  auto meta_active = [&](int b) { return reinterpret_cast<uint16_t*>(meta_row(b) + kTileM); };
+  auto meta_count = [&](int b) { return reinterpret_cast<int*>(meta_base + (size_t)b * L.meta_bytes + L.meta_bytes - 16); };
+
+  const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  // longest tiles (highest masks, last in tile order) first
+  auto tile_row0 = [&](int i) { return (int64_t)(num_tiles - 1 - ((int)blockIdx.x + i * (int)gridDim.x)) * kTileM; };
+
+  if (tid == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(smem_u32(&full_bar[s]), 128); mbar_init(smem_u32(&empty_bar[s]), 1); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&meta_full[b]), 1);
+      mbar_init(smem_u32(&meta_empty[b]), kPersistProducerWarps + 1);
+      mbar_init(smem_u32(&tmem_full[b]), 1);
+      mbar_init(smem_u32(&tmem_empty[b]), 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == kPersistProducerWarps) tmem_alloc(smem_u32(tmem_slot), p.tmem_cols);
+  {  // (offset, channel) of every 16-byte piece of every chunk: tile-independent
+    const int ktot = p.kvol * p.cin;
+    for (int i = tid; i < p.num_chunks * 8; i += kPersistThreads) {
+      const int e0 = (i >> 3) * T::kEPR + (i & 7) * T::kEPP;
+      uint32_t v = 0xffffffffu;
+      if (e0 < ktot) { const int k = e0 / p.cin; v = ((uint32_t)k << 16) | (uint32_t)(e0 - k * p.cin); }
+      kc_s[i] = v;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t acc_stride = p.tmem_cols >> 1;   // two accumulators
+
+  if (warp < kPersistProducerWarps) {
+    // ======================= producers =======================
+    const float* x = reinterpret_cast<const float*>(p.x);
+    const float* w = reinterpret_cast<const float*>(p.w);
+    const int grp = warp >> 2;
+    const int tg = tid & 127;
+    const int piece = tg & 7, rbase = tg >> 3;
+    const uint32_t tile_off = sw128_offset(rbase, piece);
+    const int nb = p.n_pad >> 4;
+    const float* zpage = reinterpret_cast<const float*>(g_zero_page);
+    const float* wrow0 = w + (uint64_t)rbase * p.w_sco32;
+    const uint64_t wstep = 16ull * p.w_sco32;
+    int gbase = 0;   // global chunk counter at the start of the tile (same in every thread)
+    for (int i = 0; i < my_tiles; ++i) {
+      const int b = i & 1;
+      mbar_wait(smem_u32(&meta_full[b]), (uint32_t)(i >> 1) & 1u);
+      const int n_active = *meta_count(b);
+      const int32_t* idx_s = meta_idx(b);
+      const uint16_t* active = meta_active(b);
+      int it = (grp - gbase % kPersistGroups + kPersistGroups) % kPersistGroups;   // first chunk of this group in the tile
+      for (; it < n_active; it += kPersistGroups) {
+        const int g = gbase + it;
+        const int s = g % p.stages;
+        const uint32_t ph = (uint32_t)(g / p.stages) & 1u;
+        const uint32_t kc = kc_s[(int)active[it] * 8 + piece];
+        const bool kvalid = kc != 0xffffffffu;
+        const uint32_t k = kvalid ? kc >> 16 : 0u;
+        const uint32_t ci = kvalid ? (kc & 0xffffu) : 0u;
+        const int32_t* idx_k = idx_s + k * kTileM;
+        float4 va[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int32_t src = kvalid ? idx_k[rbase + 16 * q] : -1;
+          const float* gp = (src >= 0) ? x + ((uint64_t)(uint32_t)src * p.x_row32 + ci) : zpage;
+          va[q] = __ldg(reinterpret_cast<const float4*>(gp));
+        }
+        const float* wk = wrow0 + ((uint64_t)k * p.w_sk32 + ci);
+        float4 vb[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int n = rbase + 16 * q;
+          const float* gp = (kvalid && q < nb && n < p.cout) ? wk + (uint64_t)q * wstep : zpage;
+          vb[q] = __ldg(reinterpret_cast<const float4*>(gp));
+        }
+        mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+        const uint32_t a_dst = smem_u32(stage_base + (size_t)s * stage_bytes) + tile_off;
+        const uint32_t b_dst = a_dst + 2 * kABytes;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) split_store(a_dst + q * 2048, kABytes, va[q]);
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          if (q < nb) split_store(b_dst + q * 2048, (uint32_t)b_bytes, vb[q]);
+        if (nb > 8) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int n = rbase + 16 * (q + 8);
+            const float* gp = (kvalid && q + 8 < nb && n < p.cout) ? wk + (uint64_t)(q + 8) * wstep : zpage;
+            vb[q] = __ldg(reinterpret_cast<const float4*>(gp));
+          }
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (q + 8 < nb) split_store(b_dst + (q + 8) * 2048, (uint32_t)b_bytes, vb[q]);
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(smem_u32(&full_bar[s]));
+      }
+      gbase += n_active;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&meta_empty[b]));   // this warp no longer reads metadata buffer b
+    }
+  } else if (warp == kPersistProducerWarps) {
+    // ======================= MMA issuer =======================
+    const uint32_t idesc = make_idesc(T::kFmt, kTileM, p.n_pad);
+    int gbase = 0;
+    for (int i = 0; i < my_tiles; ++i) {
+      const int b = i & 1;
+      mbar_wait(smem_u32(&meta_full[b]), (uint32_t)(i >> 1) & 1u);
+      const int n_active = *meta_count(b);
+      mbar_wait(smem_u32(&tmem_empty[b]), ((uint32_t)(i >> 1) & 1u) ^ 1u);   // accumulator b drained (first two: free)
+      tc_fence_after();
+      const uint32_t acc = tmem_base + (uint32_t)b * acc_stride;
+      for (int it = 0; it < n_active; ++it) {
+        const int g = gbase + it;
+        const int s = g % p.stages;
+        const uint32_t ph = (uint32_t)(g / p.stages) & 1u;
+        mbar_wait(smem_u32(&full_bar[s]), ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint64_t da = smem_desc_kmajor_sw128(smem_u32(stage_base + (size_t)s * stage_bytes));
+          const uint64_t dal = da + (uint64_t)(kABytes >> 4), dbh = dal + (uint64_t)(kABytes >> 4);
+          const uint64_t dbl = dbh + (uint64_t)(b_bytes >> 4);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            umma_tf32(acc, dal + 2 * ks, dbh + 2 * ks, idesc, (it | ks) != 0 ? 1u : 0u);
+            umma_tf32(acc, da + 2 * ks, dbl + 2 * ks, idesc, 1u);
+            umma_tf32(acc, da + 2 * ks, dbh + 2 * ks, idesc, 1u);
+          }
+          umma_commit(smem_u32(&empty_bar[s]));
+          if (it == n_active - 1) umma_commit(smem_u32(&tmem_full[b]));
+        }
+        __syncwarp();
+      }
+      if (n_active == 0 && lane == 0) mbar_arrive(smem_u32(&tmem_full[b]));   // nothing to accumulate: epilogue writes bias only
+      gbase += n_active;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&meta_empty[b]));
+    }
+    tc_fence_before();
+  } else {
+    // ======================= epilogue warps: metadata of the next tile, then drain of the current one ==========
+    const int ew = warp - kPersistProducerWarps - 1;   // 0..3: index within the epilogue group
+    const int lg = warp & 3;                           // TMEM lane group this warp may read (hardware: warp id % 4)
+    const int et = tid - (kPersistProducerWarps + 1) * 32;   // 0..127
+    auto prepare = [&](int j) {
+      const int b = j & 1;
+      mbar_wait(smem_u32(&meta_empty[b]), ((uint32_t)(j >> 1) & 1u) ^ 1u);
+      int32_t* idx_s = meta_idx(b);
+      int32_t* row_s = meta_row(b);
+      uint16_t* active = meta_active(b);
+      const int64_t row0 = tile_row0(j);
+      {
+        const int64_t pos = row0 + et;
+        int32_t jr = -1;
+        if (pos < p.n_out) jr = (p.order != nullptr) ? __ldg(&p.order[pos]) : (int32_t)pos;
+        row_s[et] = jr;
+      }
+      if (et < 4) scratch[et] = 0u;   // kmask
+      // neighbour indices: thread et owns row et of the tile for every offset; batches of 9 loads
+      const int64_t pos = row0 + et;
+      const bool in = pos < p.n_out;
+      for (int k0 = 0; k0 < p.kvol; k0 += 9) {
+        int32_t v[9];
+#pragma unroll
+        for (int u = 0; u < 9; ++u) {
+          const int k = k0 + u;
+          v[u] = -1;
+          if (k < p.kvol && in) v[u] = (p.nbr != nullptr) ? __ldg(&p.nbr[(int64_t)k * p.n_out + pos]) : (int32_t)pos;
+        }
+#pragma unroll
+        for (int u = 0; u < 9; ++u)
+          if (k0 + u < p.kvol) idx_s[(k0 + u) * kTileM + et] = v[u];
+      }
+      bar_sync_named(1, 128);
+      // which offsets have a neighbour in this tile: warp ew looks at offsets ew, ew + 4, ...
+      for (int k = ew; k < p.kvol; k += 4) {
+        const int32_t* r = idx_s + k * kTileM + lane;
+        const bool a = (r[0] >= 0) | (r[32] >= 0) | (r[64] >= 0) | (r[96] >= 0);
+        if (__any_sync(0xffffffffu, a) && lane == 0) atomicOr(&scratch[k >> 5], 1u << (k & 31));
+      }
+      bar_sync_named(1, 128);
+      const uint32_t km[4] = {scratch[0], scratch[1], scratch[2], scratch[3]};
+      int n_total = 0;
+      for (int c0 = 0; c0 < p.num_chunks; c0 += 128) {
+        const int c = c0 + et;
+        bool on = false;
+        if (c < p.num_chunks) {
+          const int k_lo = (int)(kc_s[c * 8] >> 16);
+          const uint32_t last = kc_s[c * 8 + 7];
+          const int k_hi = (last == 0xffffffffu) ? p.kvol - 1 : (int)(last >> 16);
+          for (int k = k_lo; k <= k_hi; ++k) on |= ((km[k >> 5] >> (k & 31)) & 1u) != 0;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, on);
+        if (lane == 0) scratch[4 + ew] = __popc(bal);
+        bar_sync_named(1, 128);
+        int before = 0, all = 0;
+#pragma unroll
+        for (int w2 = 0; w2 < 4; ++w2) { const int cnt = (int)scratch[4 + w2]; before += (w2 < ew) ? cnt : 0; all += cnt; }
+        if (on) active[n_total + before + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)c;
+        n_total += all;
+        bar_sync_named(1, 128);
+      }
+      if (et == 0) *meta_count(b) = n_total;
+      bar_sync_named(1, 128);   // every epilogue thread's metadata writes are done
+      if (et == 0) mbar_arrive(smem_u32(&meta_full[b]));
+    };
+    if (my_tiles > 0) prepare(0);
+    for (int i = 0; i < my_tiles; ++i) {
+      if (i + 1 < my_tiles) prepare(i + 1);
+      const int b = i & 1;
+      mbar_wait(smem_u32(&tmem_full[b]), (uint32_t)(i >> 1) & 1u);
+      tc_fence_after();
+      const int n_active = *meta_count(b);
+      const int32_t j32 = meta_row(b)[lg * 32 + lane];
+      const int64_t j = j32;
+      const uint32_t acc = tmem_base + (uint32_t)b * acc_stride + ((uint32_t)(lg * 32) << 16);
+      for (int col0 = 0; col0 < p.n_pad; col0 += 16) {
+        uint32_t v[16];
+        if (n_active > 0) {
+          tmem_ld_x16(acc + (uint32_t)col0, v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int q = 0; q < 16; ++q) v[q] = 0u;
+        }
+        if (j32 < 0) continue;
+        float f[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          const int co = col0 + q;
+          f[q] = __uint_as_float(v[q]) + ((p.bias != nullptr && co < p.cout) ? __ldg(&p.bias[co]) : 0.f);
+        }
+        fp32_row_epilogue(p, f, j, col0);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tmem_empty[b]));   // accumulator b may be overwritten
+    }
+  }
+  __syncthreads();
+  if (warp == kPersistProducerWarps) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// returns PV2_EUNSUPPORTED when the shape does not fit the persistent kernel (the caller uses the one-tile kernel)
+int launch_persistent(const GGParams& p0, cudaStream_t stream) {
+  static int enabled = -1;
+  if (enabled < 0) { const char* e = getenv("PV2_GG_PERSISTENT"); enabled = (e && e[0] == '0') ? 0 : 1; }
+  if (!enabled) return PV2_EUNSUPPORTED;
+  GGParams p = p0;
+  if (p.x_lo_off != 0) return PV2_EUNSUPPORTED;
+  p.n_pad = (p.cout + 15) / 16 * 16;
+  p.num_chunks = (p.kvol * p.cin + 31) / 32;
+  const int tiles = (int)((p.n_out + kTileM - 1) / kTileM);
+  if (tiles < 2 * PV2_SM_COUNT || p.n_pad > 256) return PV2_EUNSUPPORTED;   // few tiles: the split-K kernel
+  if (p.x_row >= (int64_t)1 << 32 || p.w_sco >= (int64_t)1 << 32 || p.w_sk >= (int64_t)1 << 32 || p.cin > 65535)
+    return PV2_EUNSUPPORTED;
+  p.x_row32 = (uint32_t)p.x_row; p.w_sco32 = (uint32_t)p.w_sco; p.w_sk32 = (uint32_t)p.w_sk;
+  p.tmem_cols = 32;
+  while ((int)p.tmem_cols < 2 * p.n_pad) p.tmem_cols <<= 1;     // two accumulators
+  if (p.tmem_cols > 512) return PV2_EUNSUPPORTED;
+  const int stage_bytes = (kABytes + p.n_pad * 128) * 2;
+  const PersistLayout L = persist_layout(p.kvol, p.num_chunks);
+  int stages = (224 * 1024 - L.fixed) / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < kPersistGroups) return PV2_EUNSUPPORTED;          // groups <= stages (mbarrier parity aliasing)
+  p.stages = stages;
+  p.ksplit = 1;
+  p.ablate = 0;
+  const size_t smem = (size_t)stages * stage_bytes + L.fixed;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(umma_gather_gemm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         227 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  const int grid = tiles < PV2_SM_COUNT ? tiles : PV2_SM_COUNT;
+  umma_gather_gemm_persistent_kernel<<<grid, kPersistThreads, smem, stream>>>(p, tiles);
+  PV2_DONE(1);
 }
 
 template <bool kSplit, bool kPre, int kGroups>
@@ -644,6 +989,11 @@ int pv2_spconv_gather_gemm_umma(const void* x, const void* w, int64_t w_sco, int
     q.w = (const char*)w + (size_t)co0 * w_sco * eb;
     q.bias = bias ? bias + co0 : nullptr;
     q.y = (char*)y + (size_t)co0 * eb;
+    if (dtype == PV2_F32) {
+      const int rp = launch_persistent(q, stream);
+      if (rp == 0) continue;
+      if (rp != PV2_EUNSUPPORTED) return rp;
+    }
     const int rc = dtype == PV2_BF16 ? launch<false, false, 2>(q, stream)
                                      : (fp32_groups(q.cout, kvol, cin) == 3 ? launch<true, false, 3>(q, stream)
                                                                             : launch<true, false, 2>(q, stream));
@@ -682,6 +1032,10 @@ int pv2_linear(const float* x, int64_t x_row, int64_t x_lo_off, int x_presplit, 
   p.y_row = y_row; p.y_lo_off = y_lo_off; p.y_split = y_split; p.act = act;
   p.y2 = y2; p.y2_row = y2_row; p.y2_lo_off = y2_lo_off;
   if (x_presplit) return launch<true, true, 2>(p, (cudaStream_t)stream_);
+  {
+    const int rp = launch_persistent(p, (cudaStream_t)stream_);
+    if (rp != PV2_EUNSUPPORTED) return rp;
+  }
   return fp32_groups(cout, 1, cin) == 3 ? launch<true, false, 3>(p, (cudaStream_t)stream_)
                                         : launch<true, false, 2>(p, (cudaStream_t)stream_);
 }

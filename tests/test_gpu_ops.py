@@ -464,3 +464,37 @@ def test_full_size_rulebook_and_conv_properties(cuda_lib):
     dx = spconv._gather_gemm(dy, wt, None, rb.tmap, n)
     lhs, rhs = (y1.double() * dy.double()).sum().item(), (x1.double() * dx.double()).sum().item()
     assert abs(lhs - rhs) < 1e-5 * (y1.double().abs() * dy.double().abs()).sum().item()
+
+
+# ------------------------------------------------------------------------------------------ dense linear (render MLP)
+@pytest.mark.parametrize("rows,cin,cout,act", [(40_000, 64, 128, 1), (40_000, 192, 68, 0), (50_001, 128, 64, 0),
+                                                (40_000, 68, 128, 3), (40_000, 64, 128, 2), (40_000, 128, 64, 4),
+                                                (700, 192, 68, 0)])
+def test_linear_matches_torch(cuda_lib, rows, cin, cout, act):
+    """pv2_linear (identity-map gather-GEMM; >= 296 row tiles take the persistent kernel, fewer the one-tile kernel)
+    against fp64 torch, including the fused SDF-decoder epilogues."""
+    from ponderv2_b200.render.fused import _linear
+    dev = _dev()
+    torch.manual_seed(rows + cin)
+    x = torch.randn(rows, cin, device=dev)
+    w = torch.randn(cout, cin, device=dev) * 0.1
+    bias = torch.randn(cout, device=dev) if act in (0, 1) else None
+    v = x.double() @ w.double().t() + (bias.double() if bias is not None else 0.0)
+    aux = torch.rand(rows, cout, device=dev)
+    y = torch.randn(rows, cout, device=dev)
+    y0 = y.clone()
+    y2 = torch.empty(rows, cout, device=dev) if act == 1 else (aux if act in (2, 3) else None)
+    _linear(x, cin, 0, False, w, bias, y, cout, 0, False, act, y2, cout, 0, rows, cin, cout)
+    if act == 0:
+        want = v
+    elif act == 1:
+        want = torch.nn.functional.softplus(v, beta=100)
+        assert (y2.double() - torch.sigmoid(100 * v)).abs().max().item() < 2e-4   # sigmoid(100 h): steep
+    elif act == 2:
+        want = v * 100 * aux.double() * (1 - aux.double())
+    elif act == 3:
+        want = y0.double() + v * aux.double()
+    else:
+        want = y0.double() + v
+    err = (y.double() - want).abs().max().item()
+    assert err < 3e-5 * max(1.0, want.abs().max().item()), err
