@@ -343,7 +343,7 @@ def run_ours(args, wl: dict) -> None:
         peaks = measured_peaks()
         gg = prof.get("pv2_spconv_gather_gemm", dict(calls=0, ms=0.0, bytes=0))
         achieved = gg["bytes"] / max(gg["ms"], 1e-9) * 1e-6 if gg["calls"] else 0.0  # GB/s
-        traffic = profiled_traffic("umma_gather_gemm_kernel")
+        traffic = profiled_traffic("umma_gather_gemm")
         line = {
             "metric": "pretrain_rays_per_sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,

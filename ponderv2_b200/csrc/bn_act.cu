@@ -69,22 +69,22 @@ __global__ void __launch_bounds__(kBnThreads) bn_partial_kernel(const float4* __
   }
 }
 
-// Combine the per-block partial sums in double, deterministically: block = 32 channels, warp w sums partial blocks
-// w, w + 8, ... (coalesced 128-byte reads), the eight warp totals are added in a fixed order.
+// Combine the per-block partial sums in double, deterministically: block = 32 channels x 32 warps, warp w sums partial
+// blocks w, w + 32, ... (coalesced 128-byte reads), the 32 warp totals are added in a fixed order.
 // MODE 0: mean / invstd (+ running statistics, torch semantics: momentum, unbiased running variance)
 // MODE 1: dgamma = sum dz * xhat, dbeta = sum dz
 template <int MODE>
-__global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restrict__ partial, int nblk, int C, int64_t N,
+__global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restrict__ partial, int nblk, int C, int64_t N,
                                                           float eps, float momentum, float* __restrict__ out_a,
                                                           float* __restrict__ out_b, float* __restrict__ running_mean,
                                                           float* __restrict__ running_var) {
-  __shared__ double s_a[8][32], s_b[8][32];
+  __shared__ double s_a[32][32], s_b[32][32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;
   double sa = 0.0, sb = 0.0;
   if (c < C) {
 #pragma unroll 4
-    for (int b = w; b < nblk; b += 8) {
+    for (int b = w; b < nblk; b += 32) {
       sa += (double)__ldg(&partial[((int64_t)b * 2) * C + c]);
       sb += (double)__ldg(&partial[((int64_t)b * 2 + 1) * C + c]);
     }
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restric
   if (w != 0 || c >= C) return;
   sa = 0.0; sb = 0.0;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { sa += s_a[i][lane]; sb += s_b[i][lane]; }
+  for (int i = 0; i < 32; ++i) { sa += s_a[i][lane]; sb += s_b[i][lane]; }
   if (MODE == 0) {
     const double m = sa / (double)N;
     double var = sb / (double)N - m * m;
@@ -186,7 +186,7 @@ int pv2_bn_act_fwd(const float* x, const float* res, const float* gamma, const f
   const int nblk = nblocks_for(n), C4 = c / 4;
   bn_partial_kernel<0><<<nblk, kBnThreads, 0, stream>>>((const float4*)x, nullptr, nullptr, nullptr, nullptr, n, C4, 0,
                                                          (float4*)workspace);
-  bn_finalize_kernel<0><<<(c + 31) / 32, 256, 0, stream>>>((const float*)workspace, nblk, c, n, eps, momentum, mean, invstd,
+  bn_finalize_kernel<0><<<(c + 31) / 32, 1024, 0, stream>>>((const float*)workspace, nblk, c, n, eps, momentum, mean, invstd,
                                                              running_mean, running_var);
   const int64_t total4 = n * C4;
   bn_apply_fwd_kernel<<<pv2_grid_for(total4, 256), 256, 0, stream>>>((const float4*)x, (const float4*)res, mean, invstd, gamma, beta,
@@ -207,7 +207,7 @@ int pv2_bn_act_bwd(const float* x, const float* dy, const float* y, const float*
   const int nblk = nblocks_for(n), C4 = c / 4;
   bn_partial_kernel<1><<<nblk, kBnThreads, 0, stream>>>((const float4*)x, (const float4*)dy, (const float4*)y, mean, invstd, n, C4,
                                                          relu, (float4*)workspace);
-  bn_finalize_kernel<1><<<(c + 31) / 32, 256, 0, stream>>>((const float*)workspace, nblk, c, n, 0.f, 0.f, dgamma, dbeta, nullptr,
+  bn_finalize_kernel<1><<<(c + 31) / 32, 1024, 0, stream>>>((const float*)workspace, nblk, c, n, 0.f, 0.f, dgamma, dbeta, nullptr,
                                                              nullptr);
   const int64_t total4 = n * C4;
   bn_apply_bwd_kernel<<<pv2_grid_for(total4, 256), 256, 0, stream>>>((const float4*)x, (const float4*)dy, (const float4*)y, mean,

@@ -1,0 +1,90 @@
+"""End-to-end parity of one pretraining step (BASELINE configs[0] shape: 2 k voxels, 128 rays x 32 samples) between the
+B200 path (`PonderIndoorStep`: backbone -> densify -> projection -> NeuS renderer -> losses, all through libpv2_b200)
+and the CPU oracle chained the same way in fp64 (oracle/spconv_oracle + densify_oracle + render_oracle).  Loss terms
+within 1e-3 relative (fp32 storage, 3xTF32 convolutions vs fp64), and the step must be trainable (finite gradients on
+every parameter the losses reach)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import densify_oracle as do
+from oracle import spconv_oracle as so
+from oracle.render_oracle import NeusOracle, RenderConfig
+from ponderv2_b200 import synth
+
+
+def _renderer_cfg(s0, si):
+    return dict(
+        type="NeuSModel",
+        field=dict(type="SDFField",
+                   sdf_decoder=dict(in_dim=64, out_dim=65, hidden_size=128, n_blocks=1, points_factor=0.0),
+                   rgb_decoder=dict(in_dim=134, out_dim=3, hidden_size=128, n_blocks=0, points_factor=0.0),
+                   beta_init=0.3, use_gradient=True, volume_type="default", padding_mode="zeros", share_volume=False,
+                   norm_pts=True, norm_padding=0.1),
+        collider=dict(type="AABBBoxCollider", near_plane=0.01, bbox=[-0.55] * 3 + [0.55] * 3),
+        sampler=dict(type="NeuSSampler", initial_sampler="UniformSampler", num_samples=s0, num_samples_importance=si,
+                     num_upsample_steps=1, train_stratified=True, single_jitter=False),
+        loss=dict(sensor_depth_truncation=0.05, temperature=0.01,
+                  weights=dict(eikonal_loss=0.01, free_space_loss=1.0, sdf_loss=10.0, depth_loss=1.0, rgb_loss=10.0,
+                               semantic_loss=0.0)))
+
+
+def test_pretrain_step_matches_oracle(cuda_lib):
+    from ponderv2_b200.pretrain import PonderIndoorStep
+    dev = torch.device("cuda:0")
+    old_tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False          # the dense projection is plain cuDNN; compare it at fp32
+    try:
+        torch.manual_seed(11)
+        n, R, s0, si = 2000, 128, 24, 8
+        grid_shape = (32, 32, 16)
+        cloud = synth.indoor_cloud(n, 1001)
+        rays = synth.ray_batch(R, 1008)
+        gc = cloud["grid_coord"]
+        rcfg = _renderer_cfg(s0, si)
+        model = PonderIndoorStep(backbone=dict(in_channels=6, num_classes=0), renderer=rcfg,
+                                 projection=dict(in_channels=96, out_channels=128), grid_shape=grid_shape,
+                                 grid_size=0.02).to(dev).train()
+        noise = {"uniform": torch.rand(R, s0 + 1), "pdf": torch.rand(R, si + 1)}
+        data = dict(grid_coord=torch.from_numpy(gc).to(dev), coord=torch.from_numpy(cloud["coord"]).to(dev),
+                    feat=torch.from_numpy(cloud["feat"]).to(dev), offset=torch.from_numpy(cloud["offset"]).to(dev),
+                    resolution=torch.tensor([int(gc.max())], dtype=torch.int64, device=dev),
+                    ray_o=torch.from_numpy(rays["rays_o"])[None].to(dev), ray_d=torch.from_numpy(rays["rays_d"])[None].to(dev),
+                    rgb=torch.from_numpy(rays["rgb"]).to(dev), depth=torch.from_numpy(rays["depth"]).to(dev))
+        sd = {k: v.detach().cpu().double() for k, v in model.state_dict().items()}   # before the step updates BN buffers
+        out = model(data, noise={k: v.to(dev) for k, v in noise.items()})
+        out["loss"].backward()
+
+        # ---- the same chain on the CPU oracle, fp64 -------------------------------------------------------------
+        bsd = {k[len("backbone."):]: v for k, v in sd.items() if k.startswith("backbone.")}
+        feats = so.spunet_forward(bsd, gc, torch.from_numpy(cloud["feat"]).double(), cloud["offset"])
+        vol = do.to_dense_indoor(torch.from_numpy(cloud["coord"]), feats, cloud["offset"],
+                                 np.array([int(gc.max())]), grid_shape, 0.02)            # (1, 96, Z, Y, X)
+        w, b = sd["proj_net.conv.0.weight"], sd["proj_net.conv.0.bias"]
+        h = torch.nn.functional.conv3d(vol, w, b, padding=1)
+        mu = h.mean(dim=(0, 2, 3, 4), keepdim=True)
+        var = h.var(dim=(0, 2, 3, 4), unbiased=False, keepdim=True)
+        g = sd["proj_net.conv.1.weight"].view(1, -1, 1, 1, 1)
+        be = sd["proj_net.conv.1.bias"].view(1, -1, 1, 1, 1)
+        vol128 = torch.relu((h - mu) / torch.sqrt(var + 1e-5) * g + be)
+        rsd = {k[len("renderer."):]: v for k, v in sd.items() if k.startswith("renderer.")}
+        cfg = RenderConfig(bbox=[-0.55] * 3 + [0.55] * 3, near_plane=0.01, num_samples=s0, num_samples_importance=si,
+                           share_volume=False, norm_pts=True, norm_padding=0.1, loss_weights=rcfg["loss"]["weights"])
+        orc = NeusOracle(rsd, cfg)
+        pred = orc.render(torch.from_numpy(rays["rays_o"]).double(), torch.from_numpy(rays["rays_d"]).double(),
+                          [vol128[0]], {k: v.double() for k, v in noise.items()}, True)
+        ld = orc.loss(pred, torch.from_numpy(rays["depth"]).double(), torch.from_numpy(rays["rgb"]).double())
+        total = orc.total_loss(ld)
+
+        for k, v in ld.items():
+            if k in out:
+                got, ref = out[k].item(), v.item()
+                assert abs(got - ref) < 1e-3 * max(1.0, abs(ref)), (k, got, ref)
+        assert abs(out["loss"].item() - total.item()) < 1e-3 * max(1.0, abs(total.item()))
+        missing = [k for k, p in model.named_parameters() if p.grad is None or not torch.isfinite(p.grad).all()]
+        # laplace_density.beta is created by the reference field but never used by the NeuS losses
+        assert all("laplace_density" in k or "fc_p" in k or "semantic" in k for k in missing), missing
+    finally:
+        torch.backends.cudnn.allow_tf32 = old_tf32
