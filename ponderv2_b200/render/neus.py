@@ -296,6 +296,15 @@ class NeuSModel(nn.Module):
                 **kwargs) -> Dict[str, torch.Tensor]:
         if not ray_bundle.origins.is_cuda:
             raise RuntimeError("NeuSModel: rays must be CUDA tensors (ponderv2_b200 has no CPU path)")
+        # The renderer always computes in fp32 (the kernels take fp32 buffers; the reference runs its sampler in fp32 too,
+        # sdf_field.py:162).  Under the trainer's autocast (engines/train.py:183-196) the folded decoder matrices would
+        # otherwise come out of `@` as half-precision tensors.
+        with torch.autocast(device_type="cuda", enabled=False):
+            volume_feature = [v.float() for v in volume_feature]
+            return self._forward_fp32(ray_bundle, volume_feature, noise, **kwargs)
+
+    def _forward_fp32(self, ray_bundle: RayBundle, volume_feature: List[torch.Tensor], noise: Optional[dict] = None,
+                      **kwargs) -> Dict[str, torch.Tensor]:
         noise = noise or {}
         rb = self.collider(ray_bundle)
         o3, d3 = rb.origins[:, None, :], rb.directions[:, None, :]
@@ -441,6 +450,10 @@ class NeuSModel(nn.Module):
         return ld
 
     def get_loss(self, preds_dict, targets):
+        with torch.autocast(device_type="cuda", enabled=False):
+            return self._get_loss_fp32(preds_dict, targets)
+
+    def _get_loss_fp32(self, preds_dict, targets):
         lw = self.loss.weights
         if lw.get("semantic_loss", 0.0) > 0:
             raise NotImplementedError("semantic (CLIP) rendering loss is SURVEY §8(f) rank 4, not in this round")
