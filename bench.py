@@ -9,8 +9,10 @@ the losses, the single gradient all-reduce (N > 1) and the optimizer step.  Prin
   value    rays/s with inputs resident in HBM (device-timed, CUDA events, max over ranks)
   e2e      same metric through the host-facing call: inputs in pinned host memory, H2D inside the timed region,
            loss read back (D2H) every step
-  roofline dominant hand-written kernel (sparse-conv gather-GEMM): algorithmic bytes / CUDA-event time, summed over its
-           launches inside the timed region, vs the measured copy bandwidth in MEASURED_PEAKS.json
+  roofline dominant hand-written kernel family (sparse-conv gather-GEMM, forward + data gradient of all 59 layers):
+           algorithmic bytes / CUDA-event time, summed over its launches inside the timed region, vs the measured copy
+           bandwidth in MEASURED_PEAKS.json; `traffic` = DRAM bytes per launch from the newest committed ncu launch list
+           (profiles/*_traffic.json, written by tools/traffic_from_launches.py)
   cpu_baseline  the CPU oracle (port of the reference path) timed on the host cores on a bounded sample
 
 `--impl reference` times the reference's own algorithm on the CPU (oracle port: spconv is not installable offline and
