@@ -15,5 +15,8 @@ Pinning status:
                            README.md:61-63), absent from /root/reference and not installable offline; the reference
                            holds no test or golden vector for it.  oracle/spconv_oracle.py restates the published
                            semantics anchored on the reference's call sites
-                           (spconv_unet_v1m1_base.py:47-66,111-119,135-142,171-177).
+                           (spconv_unet_v1m1_base.py:47-66,111-119,135-142,171-177).  Two independently written
+                           restatements exist — numpy/torch (spconv_oracle.py) and plain C (spconv_c.c, bound by
+                           c_oracle.py) — and tests/test_oracle_cpu.py requires them to agree bit-exactly on rulebooks
+                           and to 1e-12 on the fp64 convolution; a third anchor is torch's dense conv3d.
 """

@@ -96,7 +96,8 @@ def build_oracle_c() -> Path | None:
     want = _digest(srcs)
     if lib.exists() and stamp.exists() and stamp.read_text() == want:
         return lib
-    cmd = ["gcc", "-O3", "-march=native", "-fopenmp", "-shared", "-fPIC", "-o", str(lib), *map(str, srcs), "-lm"]
+    # no -march=native: the library is built in one container and may be loaded on another host
+    cmd = ["gcc", "-O3", "-fopenmp", "-shared", "-fPIC", "-o", str(lib), *map(str, srcs), "-lm"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"oracle build failed:\n{r.stderr}")

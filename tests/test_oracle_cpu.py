@@ -151,3 +151,33 @@ def test_sparse_conv_matches_dense_conv3d():
     dense_c[0, :, oi[:, 1], oi[:, 2], oi[:, 3]] = yd8.t()
     refi = torch.nn.functional.conv_transpose3d(dense_c, wi.permute(4, 0, 1, 2, 3), stride=2)
     assert torch.allclose(yi, refi[0, :, i8[:, 1], i8[:, 2], i8[:, 3]].t(), atol=1e-10)
+
+
+def test_c_restatement_agrees_with_numpy_oracle():
+    """oracle/spconv_c.c (plain C) and oracle/spconv_oracle.py (numpy/torch) were written independently from SURVEY
+    Appendix B; they must agree bit-exactly on rulebooks and to 1e-12 on the fp64 convolution."""
+    from ponderv2_b200 import build, synth
+    build.build_oracle_c()
+    from oracle import c_oracle
+    rng = np.random.default_rng(5)
+    cloud = synth.indoor_cloud(4000, 77)
+    coords = np.concatenate([np.zeros((4000, 1), np.int64), cloud["grid_coord"]], 1).astype(np.int32)
+    coords[2000:, 0] = 1                                   # two scenes in the batch
+    shape = (cloud["grid_coord"].max(0) + 96).tolist()
+    for ks in (3, 5):
+        assert np.array_equal(c_oracle.subm_rulebook(coords, shape, ks), so.subm_rulebook(coords, shape, ks))
+    oc, in2out, koff, oshape = c_oracle.down_rulebook(coords, shape)
+    rc, rin2out, rkoff, roshape = so.down_rulebook(coords, shape)
+    assert oshape == roshape and np.array_equal(oc, rc) and np.array_equal(in2out, rin2out) and np.array_equal(koff, rkoff)
+    # a tight shape: windows outside the unpadded input are dropped by both
+    tight = (cloud["grid_coord"].max(0) + 1).tolist()
+    oc2, in2, _, _ = c_oracle.down_rulebook(coords, tight)
+    rc2, rin2, _, _ = so.down_rulebook(coords, tight)
+    assert np.array_equal(oc2, rc2) and np.array_equal(in2, rin2)
+    nbr = so.subm_rulebook(coords, shape, 3)
+    x = rng.standard_normal((4000, 24))
+    w = rng.standard_normal((40, 3, 3, 3, 24)) * 0.1
+    b = rng.standard_normal(40)
+    y_c = c_oracle.sparse_conv(x, w.reshape(40, 27, 24), b, nbr)
+    y_np = so.sparse_conv(torch.from_numpy(x), torch.from_numpy(w), torch.from_numpy(b), nbr, 4000).numpy()
+    assert np.abs(y_c - y_np).max() < 1e-12 * max(1.0, np.abs(y_np).max())
