@@ -233,6 +233,21 @@ def run_reference(args, wl: dict) -> None:
 
 
 # ------------------------------------------------------------------------------------------------------------
+def build_model(wl: dict, dev):
+    """Model (identical replicas: fixed seed), flat parameter/gradient buffers, SGD as in the reference configs
+    (configs/scannet/pretrain-ponder-spunet-v1m1-0-base.py:96-98)."""
+    from ponderv2_b200.dist import FlatParameters, broadcast_parameters
+    from ponderv2_b200.pretrain import PonderIndoorStep
+    torch.manual_seed(1234)
+    model = PonderIndoorStep(backbone=dict(in_channels=6, num_classes=0), renderer=renderer_cfg(wl["s0"], wl["si"]),
+                             projection=dict(in_channels=96, out_channels=128), grid_shape=wl["grid_shape"],
+                             grid_size=0.02).to(dev).train()
+    flat = FlatParameters(model)
+    broadcast_parameters(flat)
+    opt = torch.optim.SGD(flat.optimizer_params(), lr=5e-4, momentum=0.9, weight_decay=1e-4, nesterov=True)
+    return model, flat, opt
+
+
 def run_ours(args, wl: dict) -> None:
     import torch.distributed as dist
     from ponderv2_b200 import _lib
@@ -251,13 +266,7 @@ def run_ours(args, wl: dict) -> None:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
 
-    torch.manual_seed(1234)  # identical replicas
-    model = PonderIndoorStep(backbone=dict(in_channels=6, num_classes=0), renderer=renderer_cfg(wl["s0"], wl["si"]),
-                             projection=dict(in_channels=96, out_channels=128), grid_shape=wl["grid_shape"],
-                             grid_size=0.02).to(dev).train()
-    flat = FlatParameters(model)
-    broadcast_parameters(flat)
-    opt = torch.optim.SGD(flat.optimizer_params(), lr=5e-4, momentum=0.9, weight_decay=1e-4, nesterov=True)
+    model, flat, opt = build_model(wl, dev)
 
     # per-rank scene (seed = 1000*config + scene index), kept in pinned host memory
     scene = make_scene(wl, 1000 * wl["cfg_id"] + rank)

@@ -111,6 +111,17 @@ CASES = {
     # outdoor (configs/nuscenes/pretrain-ponder-spunet-v1m1-0-base.py), shrunk
     "outdoor_train": dict(
         kind="outdoor", training=True, R=20, S0=18, Si=6, vol=(32, 5, 12, 12), seed=13),
+    # the sample counts the benchmarks run (BASELINE.json configs[1..3]): every 32-sample round of the per-ray kernels
+    # (transmittance carried across rounds) and both ends of their size limits meet the reference.  Small volumes and
+    # few rays: the sample axis is the point.
+    "indoor_train_c2": dict(      # C2 / C3: 96 coarse + 32 importance samples
+        kind="indoor", training=True, R=14, S0=96, Si=32, vol=(128, 4, 6, 8), seed=21),
+    "indoor_eval_c2": dict(
+        kind="indoor", training=False, R=8, S0=96, Si=32, vol=(128, 4, 6, 8), seed=22),
+    "indoor_train_s128": dict(    # the reference's own default is 96 + 36; 128 coarse samples = 4 full rounds
+        kind="indoor", training=True, R=10, S0=128, Si=36, vol=(128, 4, 6, 8), seed=23),
+    "outdoor_train_c4": dict(     # C4: 192 coarse + 64 importance samples = 256 = the per-ray kernels' maximum
+        kind="outdoor", training=True, R=10, S0=192, Si=64, vol=(32, 5, 12, 12), seed=24),
 }
 
 
@@ -209,9 +220,13 @@ def gen_spunet_state() -> None:
 def main() -> None:
     GOLD.mkdir(parents=True, exist_ok=True)
     Dict = _install_stubs()
+    only = set(sys.argv[1:])
     for name, spec in CASES.items():
+        if only and name not in only:
+            continue
         gen_render_case(name, spec, Dict)
-    gen_spunet_state()
+    if not only or "spunet_state" in only:
+        gen_spunet_state()
 
 
 if __name__ == "__main__":

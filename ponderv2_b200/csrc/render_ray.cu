@@ -17,8 +17,8 @@
 namespace {
 
 constexpr int kWarpsPerBlock = 4;
-constexpr int kMaxS0 = 128;      // coarse samples per ray
-constexpr int kMaxNb = 64;       // importance bins per ray (Si + 1)
+constexpr int kMaxS0 = 256;      // coarse samples per ray (C4: 192)
+constexpr int kMaxNb = 128;      // importance bins per ray (Si + 1; C4: 65)
 constexpr int kMaxRounds = 8;    // S <= 256 fine samples per ray
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }

@@ -85,6 +85,10 @@ class PonderIndoorStep(nn.Module):
 
     def forward(self, data_dict: Dict[str, torch.Tensor], noise: Optional[dict] = None) -> Dict[str, torch.Tensor]:
         data_dict["sparse_backbone_feat"] = self.backbone(data_dict)
+        return self.forward_after_backbone(data_dict, noise)
+
+    def forward_after_backbone(self, data_dict: Dict[str, torch.Tensor], noise: Optional[dict] = None) -> Dict[str, torch.Tensor]:
+        """densify -> projection -> render -> losses, given `sparse_backbone_feat` (extract_feature's output)."""
         volume = self.proj_net(self.to_dense(data_dict))            # (B,C,Z,Y,X), channels_last_3d
         outs = []
         scene_vols = _SceneViews.apply(volume)

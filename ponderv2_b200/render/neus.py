@@ -25,6 +25,17 @@ from ..smooth_sampler import SmoothSampler
 from . import fused, ray
 
 
+_NOTED = set()
+
+
+def _note_once(key: str, msg: str) -> None:
+    """One warning per process and reason when a configuration leaves the hand-written fast path (never silent)."""
+    if key not in _NOTED:
+        _NOTED.add(key)
+        import warnings
+        warnings.warn(msg, RuntimeWarning, stacklevel=3)
+
+
 class RayBundle:
     """origins [R,3], directions [R,3] (+ nears/fars [R,1] once collided); rays.py:108-116."""
 
@@ -164,8 +175,8 @@ class SDFField(nn.Module):
         pc, nc = torch.sigmoid(prv * inv_s), torch.sigmoid(nxt * inv_s)
         return ((pc - nc + 1e-5) / (pc + 1e-5)).clip(0.0, 1.0)
 
-    def forward(self, points, directions, deltas, volume_feature, return_alphas=True):
-        if self.norm_pts:
+    def forward(self, points, directions, deltas, volume_feature, return_alphas=True, normalized=False):
+        if self.norm_pts and not normalized:
             points = points / (1 + self.norm_padding + 10e-4) + 0.5
             points = torch.where(points >= 1, torch.full_like(points, 1 - 10e-4), points)
             points = torch.where(points < 0, torch.zeros_like(points), points)
@@ -314,9 +325,20 @@ class NeuSModel(nn.Module):
         R = rb.origins.shape[0]
         use_fused = (self.use_fused and fused.eligible(self.field) and len(volume_feature) == 1
                      and volume_feature[0].shape[0] == 128)
-        if use_fused and self.use_ray_kernels and ray.supported(smp.num_samples, smp.num_samples_importance,
-                                                                smp.num_upsample_steps):
+        can_ray = self.use_ray_kernels and ray.supported(smp.num_samples, smp.num_samples_importance,
+                                                         smp.num_upsample_steps)
+        if self.use_fused and not use_fused:
+            _note_once("field", "NeuSModel: this field configuration is not the indoor one the tensor-core field kernels "
+                       "are written for (sdf 64->128->65, rgb 134->128->3, C = 128, share_volume=False); the SDF/colour "
+                       "MLPs run as torch linears around the CUDA trilinear sampler")
+        if self.use_ray_kernels and not can_ray:
+            _note_once("ray", f"NeuSModel: sampler {smp.num_samples}+{smp.num_samples_importance} x "
+                       f"{smp.num_upsample_steps} steps is outside the per-ray kernels' limits ({ray.MAX_S0}+{ray.MAX_SI}, "
+                       f"total {ray.MAX_S}, one upsample step); sampling and compositing run as torch ops")
+        if use_fused and can_ray:
             return self._forward_ray_kernels(rb, volume_feature[0], noise)
+        if can_ray:
+            return self._forward_ray_kernels_generic(rb, volume_feature, noise)
         if use_fused:
             vol_cl = volume_feature[0].permute(1, 2, 3, 0).contiguous().float()  # free for channels_last_3d volumes
             fp = fused.fold_parameters(self.field)
@@ -423,6 +445,47 @@ class NeuSModel(nn.Module):
         return dict(rgb=rgb, depth=depth[:, None], normal=normal, weights=weights[..., None], sdf=sdf_f[..., None],
                     gradients=grad_f, z_vals=z, sampled_points=o3 + d3 * z, init_sampled_points=pts_c,
                     init_weights=init_w[..., None], new_sampled_points=o3 + d3 * new_e[..., None])
+
+    def _forward_ray_kernels_generic(self, rb: RayBundle, volume_feature: List[torch.Tensor], noise: dict):
+        """Any field configuration (outdoor: sdf 32->16x5->17, no colour head; ponder_outdoor_base.py:218-251): the
+        per-ray kernels do collider / sampler / compositing, the field is SDFField.forward (torch linears around the
+        twice-differentiable CUDA sampler, autograd supplies d sdf / d p as in sdf_field.py:226-238)."""
+        smp, fld = self.sampler, self.field
+        o, d = rb.origins, rb.directions
+        R, S0, Si = o.shape[0], smp.num_samples, smp.num_samples_importance
+        S = S0 + Si
+        jitter = smp.train_stratified and self.training
+        nz_u = nz_p = None
+        if jitter:
+            nz_u = noise.get("uniform")
+            if nz_u is None:
+                nz_u = torch.rand((R, 1 if smp.single_jitter else S0 + 1), dtype=torch.float32, device=o.device)
+            nz_p = noise.get("pdf")
+            if nz_p is None:
+                nz_p = torch.rand((R, 1 if smp.single_jitter else Si + 1), dtype=torch.float32, device=o.device)
+        nears, fars, bins, pts_c = ray.ray_setup(o, d, S0, self.collider.bbox, self.collider.near_plane, nz_u)
+        rb.nears, rb.fars = nears, fars
+        with torch.no_grad():   # coarse pass: un-normalised points, as the reference's sampler calls get_sdf directly
+            sdf_c = fld.get_sdf(pts_c, volume_feature)[0].squeeze(-1)
+        starts, deltas, pn, init_w, new_bins, minmax = ray.ray_resample(
+            o, d, nears, fars, bins, sdf_c, Si, smp.base_variance, nz_p, fld.norm_pts, fld.norm_padding)
+        dirs = d[:, None, :].expand(-1, S, -1)
+        fo = fld(pn, dirs, deltas[..., None], volume_feature, return_alphas=False, normalized=True)
+        rgbs = fo["rgb"] if "rgb" in fo else None
+        weights, rgb, depth, normal = ray.RayComposite.apply(
+            fo["sdf"].squeeze(-1), fo["gradients"], rgbs, fld.deviation_network.variance, starts, deltas, d, minmax,
+            fld._cos_anneal_ratio, not self.training)
+        o3, d3 = o[:, None, :], d[:, None, :]
+        z = starts[..., None]
+        new_e = new_bins * fars + (1 - new_bins) * nears
+        out = dict(depth=depth[:, None], normal=normal, weights=weights[..., None], sdf=fo["sdf"],
+                   gradients=fo["gradients"], z_vals=z, sampled_points=o3 + d3 * z, init_sampled_points=pts_c,
+                   init_weights=init_w[..., None], new_sampled_points=o3 + d3 * new_e[..., None])
+        if rgb is not None:
+            out["rgb"] = rgb
+        if "semantic" in fo:
+            out["semantic"] = (weights[..., None] * fo["semantic"]).sum(-2)
+        return out
 
     def _fused_loss(self, preds_dict, targets):
         lw = self.loss.weights

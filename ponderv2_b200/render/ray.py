@@ -11,7 +11,7 @@ import torch
 
 from .. import _lib
 
-MAX_S0, MAX_SI, MAX_S = 128, 63, 256
+MAX_S0, MAX_SI, MAX_S = 256, 127, 256   # kMaxS0, kMaxNb - 1, 32 * kMaxRounds in csrc/render_ray.cu
 
 
 def supported(s0: int, si: int, steps: int) -> bool:

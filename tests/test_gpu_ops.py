@@ -263,6 +263,8 @@ def test_spunet_backbone_matches_oracle(cuda_lib):
         if e > worst:
             worst, worst_name = e, name
     joint = (num / den) ** 0.5
+    from tests.conftest import record
+    record("spunet_backbone_matches_oracle", fwd=err, grad_joint=joint, grad_worst=worst, worst_name=worst_name)
     print("backbone grad err: joint", joint, "worst", worst_name, worst)
     assert joint < 2e-2, joint
     assert worst < 0.2, (worst_name, worst)
@@ -464,6 +466,50 @@ def test_full_size_rulebook_and_conv_properties(cuda_lib):
     dx = spconv._gather_gemm(dy, wt, None, rb.tmap, n)
     lhs, rhs = (y1.double() * dy.double()).sum().item(), (x1.double() * dx.double()).sum().item()
     assert abs(lhs - rhs) < 1e-5 * (y1.double().abs() * dy.double().abs()).sum().item()
+
+
+@pytest.mark.parametrize("cin,cout", [(32, 32), (96, 96), (256, 256), (128, 96)])
+def test_full_size_conv_matches_oracle(cuda_lib, cin, cout):
+    """BASELINE configs[1] size: SubMConv3d on the 100 k-voxel scene against the fp64 oracle — forward, data gradient
+    and weight gradient — so that the kernels the benchmark actually launches (782 row tiles: the persistent
+    gather-GEMM for the wide layers, two resident one-tile CTAs for the narrow ones, the row-chunked weight gradient)
+    meet the oracle on a real rulebook, not only each other.  The forward is also checked against the independent
+    plain-C restatement (oracle/spconv_c.c)."""
+    import ponderv2_b200.spconv.pytorch as spconv
+    from oracle import c_oracle
+    from tests.conftest import record
+    dev = _dev()
+    n = 100_000
+    ind, shape = _indoor_indices(n, 2000)
+    torch.manual_seed(cin * 7 + cout)
+    mod = spconv.SubMConv3d(cin, cout, 3, padding=1, bias=True, indice_key="k").to(dev)
+    with torch.no_grad():
+        mod.weight.normal_(0.0, 0.05)
+        mod.bias.normal_(0.0, 0.1)
+    x64 = torch.randn(n, cin, dtype=torch.float64)
+    g64 = torch.randn(n, cout, dtype=torch.float64)
+    xg = x64.to(dev, torch.float32).requires_grad_(True)
+    out = mod(spconv.SparseConvTensor(xg, torch.from_numpy(ind).to(dev), shape, 1)).features
+    out.backward(g64.to(dev, torch.float32))
+    w64 = mod.weight.detach().cpu().double().requires_grad_(True)
+    b64 = mod.bias.detach().cpu().double().requires_grad_(True)
+    xo = x64.clone().requires_grad_(True)
+    yo = so.subm_conv(so.OracleSparseTensor(xo, ind, shape, 1), w64, b64, 3, "k").features
+    yo.backward(g64)
+    yc = c_oracle.sparse_conv(x64.numpy(), w64.detach().reshape(cout, 27, cin).numpy(), b64.detach().numpy(),
+                              so.subm_rulebook(ind, shape, 3))
+    assert np.abs(yc - yo.detach().numpy()).max() < 1e-10 * max(1.0, float(yo.abs().max()))
+    scale = lambda t: max(t.abs().max().item(), 1e-6)
+    errs = {
+        "y": (out.detach().cpu().double() - yo.detach()).abs().max().item() / scale(yo),
+        "dx": (xg.grad.cpu().double() - xo.grad).abs().max().item() / scale(xo.grad),
+        "dw": (mod.weight.grad.cpu().double() - w64.grad).abs().max().item() / scale(w64.grad),
+        "db": (mod.bias.grad.cpu().double() - b64.grad).abs().max().item() / scale(b64.grad),
+    }
+    record("full_size_conv_matches_oracle", cin=cin, cout=cout, **errs)
+    # fp32 storage, fp32-grade tensor-core products, fp32 accumulation over 27 * cin terms (y, dx) / ~1e5 rows (dw, db)
+    for k, v in errs.items():
+        assert v < 1e-4, (k, v, errs)
 
 
 # ------------------------------------------------------------------------------------------ dense linear (render MLP)

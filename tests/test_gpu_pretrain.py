@@ -54,6 +54,10 @@ def test_pretrain_step_matches_oracle(cuda_lib):
                     ray_o=torch.from_numpy(rays["rays_o"])[None].to(dev), ray_d=torch.from_numpy(rays["rays_d"])[None].to(dev),
                     rgb=torch.from_numpy(rays["rgb"]).to(dev), depth=torch.from_numpy(rays["depth"]).to(dev))
         sd = {k: v.detach().cpu().double() for k, v in model.state_dict().items()}   # before the step updates BN buffers
+        pnames = {k for k, _ in model.named_parameters()}
+        for k, v in sd.items():
+            if k in pnames:
+                v.requires_grad_(True)
         out = model(data, noise={k: v.to(dev) for k, v in noise.items()})
         out["loss"].backward()
 
@@ -77,6 +81,7 @@ def test_pretrain_step_matches_oracle(cuda_lib):
                           [vol128[0]], {k: v.double() for k, v in noise.items()}, True)
         ld = orc.loss(pred, torch.from_numpy(rays["depth"]).double(), torch.from_numpy(rays["rgb"]).double())
         total = orc.total_loss(ld)
+        total.backward()
 
         for k, v in ld.items():
             if k in out:
@@ -86,5 +91,26 @@ def test_pretrain_step_matches_oracle(cuda_lib):
         missing = [k for k, p in model.named_parameters() if p.grad is None or not torch.isfinite(p.grad).all()]
         # laplace_density.beta is created by the reference field but never used by the NeuS losses
         assert all("laplace_density" in k or "fc_p" in k or "semantic" in k for k in missing), missing
+        # parameter gradients of the whole step against the fp64 chain: renderer + projection tensors individually,
+        # the backbone jointly (its deepest levels normalise over a few dozen rows, see test_spunet_backbone_matches_oracle)
+        from tests.conftest import record
+        num = den = 0.0
+        worst_r, worst_r_name = 0.0, ""
+        for k, p in model.named_parameters():
+            ref = sd[k].grad
+            if ref is None or p.grad is None:
+                continue
+            d = p.grad.detach().cpu().double() - ref
+            if k.startswith("backbone."):
+                num += d.pow(2).sum().item(); den += ref.pow(2).sum().item()
+            else:
+                e = d.norm().item() / max(ref.norm().item(), 1e-12)
+                if e > worst_r:
+                    worst_r, worst_r_name = e, k
+        joint_b = (num / max(den, 1e-300)) ** 0.5
+        record("pretrain_step_matches_oracle", loss=out["loss"].item(), loss_ref=total.item(),
+               grad_renderer_projection_worst=worst_r, worst_name=worst_r_name, grad_backbone_joint=joint_b)
+        assert worst_r < 5e-3, (worst_r_name, worst_r)
+        assert joint_b < 2e-2, joint_b
     finally:
         torch.backends.cudnn.allow_tf32 = old_tf32

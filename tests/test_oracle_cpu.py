@@ -37,7 +37,8 @@ def test_trilinear_oracle_gradgradcheck(padding_mode, smooth):
 
 
 # --- renderer oracle vs the reference's own NeuSModel ---------------------------------------------------------
-@pytest.mark.parametrize("case", ["indoor_train", "indoor_eval", "outdoor_train"])
+@pytest.mark.parametrize("case", ["indoor_train", "indoor_eval", "outdoor_train", "indoor_train_c2", "indoor_eval_c2",
+                                  "indoor_train_s128", "outdoor_train_c4"])
 def test_render_oracle_matches_reference(case):
     meta, arr, sd, cfg = load_render_case(case)
     for p in sd.values():
