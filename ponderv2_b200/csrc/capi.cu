@@ -14,7 +14,7 @@ void pv2_note_launches(int n) { __atomic_fetch_add(&g_launches, (unsigned long l
 int64_t pv2_launch_count(void) { return (int64_t)__atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
 int pv2_spconv_gather_gemm_umma(const void*, const void*, int64_t, int64_t, const float*, const int32_t*, const int32_t*,
-                                void*, int64_t, int64_t, int, int, int, int, void*);
+                                void*, int64_t, int64_t, int, int, int, int, void*, size_t, void*);
 
 static int force_simt() {
   static int v = -1;
@@ -43,12 +43,11 @@ int pv2_sm_count(void) {
 int pv2_spconv_gather_gemm(const void* x, const void* w, int64_t w_sco, int64_t w_sk, const float* bias,
                            const int32_t* nbr, const int32_t* row_order, void* y, int64_t n_in, int64_t n_out, int cin,
                            int cout, int kvol, int dtype, void* workspace, size_t workspace_bytes, void* stream) {
-  (void)workspace; (void)workspace_bytes;
   // tensor-core implicit GEMM whenever the shape allows it (16-byte aligned channel runs, Cout <= 256, K <= 32);
   // the ragged stem (Cin = 6 / 4, K = 125) runs on the exact-fp32 SIMT kernel.  PV2_FORCE_SIMT=1 is for A/B tests.
   if (!force_simt() && (int64_t)cin * kvol >= 64) {
     int rc = pv2_spconv_gather_gemm_umma(x, w, w_sco, w_sk, bias, nbr, row_order, y, n_in, n_out, cin, cout, kvol, dtype,
-                                         stream);
+                                         workspace, workspace_bytes, stream);
     if (rc != PV2_EUNSUPPORTED) return rc;
   }
   return pv2_spconv_gather_gemm_simt(x, w, w_sco, w_sk, bias, nbr, row_order, y, n_in, n_out, cin, cout, kvol, dtype, stream);
@@ -57,9 +56,19 @@ int pv2_spconv_gather_gemm(const void* x, const void* w, int64_t w_sco, int64_t 
 int pv2_wgrad_umma(const float*, int64_t, int64_t, const float*, int64_t, int64_t, const int32_t*, const int32_t*,
                    const uint8_t*, float*, int64_t, int64_t, int, int, int, void*, size_t, void*);
 
+int pv2_wgrad_mn(const void*, const void*, const int32_t*, const int32_t*, const uint8_t*, float*, int64_t, int64_t, int, int,
+                 int, int, void*);
+
 int pv2_spconv_wgrad(const void* x, const void* dy, const int32_t* nbr, const int32_t* row_order,
                      const uint8_t* blk_active, float* dw, int64_t n_in, int64_t n_out, int cin, int cout, int kvol,
                      int dtype, void* workspace, size_t workspace_bytes, void* stream) {
+  // second-generation kernel: MN-major bf16 operands (fp32 storage as bf16x3), no transposes, no scratch
+  static int use_mn = -1;
+  if (use_mn < 0) { const char* e = getenv("PV2_WGRAD_MN"); use_mn = (e && e[0] == '0') ? 0 : 1; }   // development A/B switch
+  if (!force_simt() && use_mn) {
+    int rc = pv2_wgrad_mn(x, dy, nbr, row_order, blk_active, dw, n_in, n_out, cin, cout, kvol, dtype, stream);
+    if (rc != PV2_EUNSUPPORTED) return rc;
+  }
   // tensor-core wgrad pays off once the gathered rows are wide (measured on B200, 100 k voxels, K = 27:
   // 96->96 1.6 vs 2.4 ms, 256->256 6.4 vs 10.1 ms, but 32->32 1.1 vs 0.6 ms): narrow layers stay on the SIMT kernel
   static int min_cin = -1;

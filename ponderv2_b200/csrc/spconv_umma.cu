@@ -24,7 +24,9 @@
 // HBM-side algorithmic bytes per call: N*Cin*b + N*Cout*b + K*Cin*Cout*b + 4*K*N.
 #include "pv2_common.cuh"
 #include "umma.cuh"
+#include <cuda.h>   // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, no libcuda link)
 #include <stdlib.h>
+#include <string.h>
 
 namespace {
 
@@ -62,6 +64,9 @@ struct GGParams {
   int ablate;        // development only (PV2_GG_ABLATE): 1 skip the global loads, 2 skip split + st.shared, 4 skip the MMAs
   int ksplit;        // > 1: gridDim.y CTAs share one row tile, each reduces a slice of the contraction and adds its
                      // partial result into the (pre-zeroed) output with red.global.add (small deep U-Net levels)
+  // bf16x3 mode (persistent kernel): weights pre-split into bf16 hi / lo matrices [2][w2_rows][ktot64], fetched by TMA
+  int w2_row0;       // first weight row (output channel) of this launch's column slice
+  int w2_rows;       // rows of one half (hi rows [0, w2_rows), lo rows [w2_rows, 2 w2_rows))
 };
 
 template <bool kSplit>
@@ -569,8 +574,35 @@ __device__ __forceinline__ void bar_sync_named(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-__global__ void __launch_bounds__(kPersistThreads) umma_gather_gemm_persistent_kernel(const GGParams p, int num_tiles) {
-  using T = ModeTraits<true>;
+// fp32 -> two bf16 halves (round to nearest): v = hi + lo + O(2^-18 |v|).  Packs 8 values into one 16-byte piece each.
+__device__ __forceinline__ void split_store_bf16(uint32_t addr, uint32_t lo_delta, const float4& v0, const float4& v1) {
+  const float f[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+  uint32_t hp[4], lp[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    const float2 hf = __bfloat1622float2(h2);
+    const __nv_bfloat162 l2 = __floats2bfloat162_rn(f[2 * i] - hf.x, f[2 * i + 1] - hf.y);
+    hp[i] = *reinterpret_cast<const uint32_t*>(&h2);
+    lp[i] = *reinterpret_cast<const uint32_t*>(&l2);
+  }
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(hp[0]), "r"(hp[1]), "r"(hp[2]), "r"(hp[3]) : "memory");
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr + lo_delta), "r"(lp[0]), "r"(lp[1]), "r"(lp[2]), "r"(lp[3]) : "memory");
+}
+
+// kBx3 = false: 3xTF32 (operands split into TF32 halves, 32 channels per 128-byte chunk, weights through registers).
+// kBx3 = true : bf16x3 -- fp32 storage, every operand split on chip into two bf16 halves (hi + lo carries 16 significand
+//   bits, products hi*hi + lo*hi + hi*lo, fp32 accumulation in TMEM).  Against 3xTF32 this halves the shared-memory bytes
+//   per channel (the pipe that bounded the TF32 kernel: 57.6 % L1/TEX, profiles/r1m) and doubles the tensor rate, at a
+//   per-product rounding of <= 3 * 2^-18 instead of 2^-20; in both modes the observed error is set by the tensor core's
+//   truncating fp32 accumulation (~ n_steps * 2^-24).  The weight operand is pre-split once per call into bf16 hi / lo
+//   matrices [Cout][K * Cin] and arrives by TMA (one 2-D box of n_pad rows x 128 B per half and chunk, hardware swizzle),
+//   so the producer warps only gather activations.
+template <bool kBx3>
+__global__ void __launch_bounds__(kPersistThreads) umma_gather_gemm_persistent_kernel(const GGParams p, int num_tiles,
+                                                                                      const __grid_constant__ CUtensorMap wmap) {
+  constexpr int kEPR = kBx3 ? 64 : 32;   // contraction elements per 128-byte operand row (chunk)
+  constexpr int kEPP = kBx3 ? 8 : 4;     // ... per 16-byte piece
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -613,12 +645,13 @@ __global__ void __launch_bounds__(kPersistThreads) umma_gather_gemm_persistent_k
   {  // (offset, channel) of every 16-byte piece of every chunk: tile-independent
     const int ktot = p.kvol * p.cin;
     for (int i = tid; i < p.num_chunks * 8; i += kPersistThreads) {
-      const int e0 = (i >> 3) * T::kEPR + (i & 7) * T::kEPP;
+      const int e0 = (i >> 3) * kEPR + (i & 7) * kEPP;
       uint32_t v = 0xffffffffu;
       if (e0 < ktot) { const int k = e0 / p.cin; v = ((uint32_t)k << 16) | (uint32_t)(e0 - k * p.cin); }
       kc_s[i] = v;
     }
   }
+  if (kBx3 && tid == 0) tma_prefetch_desc(&wmap);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -654,6 +687,30 @@ __global__ void __launch_bounds__(kPersistThreads) umma_gather_gemm_persistent_k
         const uint32_t k = kvalid ? kc >> 16 : 0u;
         const uint32_t ci = kvalid ? (kc & 0xffffu) : 0u;
         const int32_t* idx_k = idx_s + k * kTileM;
+        if constexpr (kBx3) {
+          // 8 rows x one 8-channel piece (32 B of fp32 = two 128-bit loads) per thread; every load is issued before
+          // the stage wait, the split + stores follow it
+          float4 va[16];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int32_t src = kvalid ? idx_k[rbase + 16 * q] : -1;
+            const float* gp = (src >= 0) ? x + ((uint64_t)(uint32_t)src * p.x_row32 + ci) : zpage;
+            va[2 * q] = __ldg(reinterpret_cast<const float4*>(gp));
+            va[2 * q + 1] = __ldg(reinterpret_cast<const float4*>(gp) + 1);
+          }
+          mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+          const uint32_t a_dst = smem_u32(stage_base + (size_t)s * stage_bytes) + tile_off;
+          if (tg == 0) {   // the weight halves of this chunk: two TMA boxes (n_pad rows x 128 B), hardware-swizzled
+            const uint32_t bar = smem_u32(&full_bar[s]);
+            const uint32_t b_dst0 = smem_u32(stage_base + (size_t)s * stage_bytes) + 2 * kABytes;
+            mbar_expect_tx(bar, 2u * (uint32_t)b_bytes);
+            const int32_t col = (int32_t)active[it] * kEPR;
+            tma_load_2d(b_dst0, &wmap, bar, col, p.w2_row0);
+            tma_load_2d(b_dst0 + (uint32_t)b_bytes, &wmap, bar, col, p.w2_rows + p.w2_row0);
+          }
+#pragma unroll
+          for (int q = 0; q < 8; ++q) split_store_bf16(a_dst + q * 2048, kABytes, va[2 * q], va[2 * q + 1]);
+        } else {
         float4 va[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -688,6 +745,7 @@ __global__ void __launch_bounds__(kPersistThreads) umma_gather_gemm_persistent_k
           for (int q = 0; q < 8; ++q)
             if (q + 8 < nb) split_store(b_dst + (q + 8) * 2048, (uint32_t)b_bytes, vb[q]);
         }
+        }
         fence_proxy_async_smem();
         mbar_arrive(smem_u32(&full_bar[s]));
       }
@@ -697,7 +755,7 @@ __global__ void __launch_bounds__(kPersistThreads) umma_gather_gemm_persistent_k
     }
   } else if (warp == kPersistProducerWarps) {
     // ======================= MMA issuer =======================
-    const uint32_t idesc = make_idesc(T::kFmt, kTileM, p.n_pad);
+    const uint32_t idesc = make_idesc(kBx3 ? 1 : 2, kTileM, p.n_pad);
     int gbase = 0;
     for (int i = 0; i < my_tiles; ++i) {
       const int b = i & 1;
@@ -718,9 +776,15 @@ __global__ void __launch_bounds__(kPersistThreads) umma_gather_gemm_persistent_k
           const uint64_t dbl = dbh + (uint64_t)(b_bytes >> 4);
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
-            umma_tf32(acc, dal + 2 * ks, dbh + 2 * ks, idesc, (it | ks) != 0 ? 1u : 0u);
-            umma_tf32(acc, da + 2 * ks, dbl + 2 * ks, idesc, 1u);
-            umma_tf32(acc, da + 2 * ks, dbh + 2 * ks, idesc, 1u);
+            if constexpr (kBx3) {
+              umma_bf16(acc, dal + 2 * ks, dbh + 2 * ks, idesc, (it | ks) != 0 ? 1u : 0u);
+              umma_bf16(acc, da + 2 * ks, dbl + 2 * ks, idesc, 1u);
+              umma_bf16(acc, da + 2 * ks, dbh + 2 * ks, idesc, 1u);
+            } else {
+              umma_tf32(acc, dal + 2 * ks, dbh + 2 * ks, idesc, (it | ks) != 0 ? 1u : 0u);
+              umma_tf32(acc, da + 2 * ks, dbl + 2 * ks, idesc, 1u);
+              umma_tf32(acc, da + 2 * ks, dbh + 2 * ks, idesc, 1u);
+            }
           }
           umma_commit(smem_u32(&empty_bar[s]));
           if (it == n_active - 1) umma_commit(smem_u32(&tmem_full[b]));
@@ -841,17 +905,80 @@ __global__ void __launch_bounds__(kPersistThreads) umma_gather_gemm_persistent_k
 }
 
 // returns PV2_EUNSUPPORTED when the shape does not fit the persistent kernel (the caller uses the one-tile kernel)
-int launch_persistent(const GGParams& p0, cudaStream_t stream) {
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: remember it per (kernel, device)
+template <typename K>
+cudaError_t ensure_smem_optin(K kernel, bool (&done)[64]) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e == cudaSuccess && dev >= 0 && dev < 64) done[dev] = true;
+  return e;
+}
+
+// ---- bf16x3 weights: [2][rows][cols] bf16 (hi half, then lo half), rows = Cout rounded up to 16, cols = K * Cin rounded up
+// to 64, zero padded.  One small kernel per convolution call (<= 1.8 M weights) and one TMA descriptor over the result.
+__global__ void presplit_weights_bf16_kernel(const float* __restrict__ w, int64_t w_sco, int64_t w_sk, int cout, int kvol,
+                                             int cin, __nv_bfloat16* __restrict__ out, int rows, int cols) {
+  const int64_t total = (int64_t)rows * cols;
+  const int ktot = kvol * cin;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols), c = (int)(i - (int64_t)r * cols);
+    float v = 0.f;
+    if (r < cout && c < ktot) {
+      const int k = c / cin;
+      v = __ldg(&w[(int64_t)r * w_sco + (int64_t)k * w_sk + (c - k * cin)]);
+    }
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    out[i] = h;
+    out[total + i] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn tensor_map_encoder() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qr) == cudaSuccess &&
+        qr == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+// 2-D bf16 matrix [rows][cols] (row-major, cols % 8 == 0), boxes of box_rows x 64 columns (128 B), 128-byte swizzle
+int encode_bf16_map(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int box_rows) {
+  EncodeTiledFn enc = tensor_map_encoder();
+  if (enc == nullptr) return PV2_EUNSUPPORTED;
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  const cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1u, 1u};
+  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : PV2_EUNSUPPORTED;
+}
+
+// returns PV2_EUNSUPPORTED when the shape does not fit the persistent kernel (the caller uses the one-tile kernel).
+// w2 != nullptr selects the bf16x3 mode: the pre-split weights [2][w2_rows][w2_cols] (p.w2_row0 = this slice's first row).
+int launch_persistent(const GGParams& p0, cudaStream_t stream, const void* w2 = nullptr, int w2_cols = 0) {
   static int enabled = -1;
   if (enabled < 0) { const char* e = getenv("PV2_GG_PERSISTENT"); enabled = (e && e[0] == '0') ? 0 : 1; }
   if (!enabled) return PV2_EUNSUPPORTED;
+  const bool bx3 = w2 != nullptr;
   GGParams p = p0;
   if (p.x_lo_off != 0) return PV2_EUNSUPPORTED;
   p.n_pad = (p.cout + 15) / 16 * 16;
-  p.num_chunks = (p.kvol * p.cin + 31) / 32;
+  p.num_chunks = bx3 ? (p.kvol * p.cin + 63) / 64 : (p.kvol * p.cin + 31) / 32;
   const int tiles = (int)((p.n_out + kTileM - 1) / kTileM);
-  if (tiles < 2 * PV2_SM_COUNT || p.n_pad > 256) return PV2_EUNSUPPORTED;   // few tiles: the split-K kernel
-  {
+  if (p.n_pad > 256) return PV2_EUNSUPPORTED;
+  if (!bx3) {
+    if (tiles < 2 * PV2_SM_COUNT) return PV2_EUNSUPPORTED;   // few tiles: the split-K kernel
     // narrow layers fit two one-tile CTAs per SM, which overlaps tiles just as well and measured faster (63 vs 73 us at
     // 100 k voxels, 32 -> 32); the persistent kernel is for the layers that shared memory limits to one CTA per SM
     const int sb = (kABytes + p.n_pad * 128) * 2;
@@ -873,15 +1000,22 @@ int launch_persistent(const GGParams& p0, cudaStream_t stream) {
   p.ksplit = 1;
   p.ablate = 0;
   const size_t smem = (size_t)stages * stage_bytes + L.fixed;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(umma_gather_gemm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         227 * 1024);
-    if (e != cudaSuccess) return (int)e;
-    attr_set = true;
-  }
   const int grid = tiles < PV2_SM_COUNT ? tiles : PV2_SM_COUNT;
-  umma_gather_gemm_persistent_kernel<<<grid, kPersistThreads, smem, stream>>>(p, tiles);
+  CUtensorMap wmap;
+  memset(&wmap, 0, sizeof(wmap));
+  if (bx3) {
+    static bool done[64] = {};
+    cudaError_t e = ensure_smem_optin(umma_gather_gemm_persistent_kernel<true>, done);
+    if (e != cudaSuccess) return (int)e;
+    const int rc = encode_bf16_map(&wmap, w2, 2 * (int64_t)p.w2_rows, w2_cols, p.n_pad);
+    if (rc != 0) return rc;
+    umma_gather_gemm_persistent_kernel<true><<<grid, kPersistThreads, smem, stream>>>(p, tiles, wmap);
+  } else {
+    static bool done[64] = {};
+    cudaError_t e = ensure_smem_optin(umma_gather_gemm_persistent_kernel<false>, done);
+    if (e != cudaSuccess) return (int)e;
+    umma_gather_gemm_persistent_kernel<false><<<grid, kPersistThreads, smem, stream>>>(p, tiles, wmap);
+  }
   PV2_DONE(1);
 }
 
@@ -909,12 +1043,10 @@ int launch(const GGParams& p0, cudaStream_t stream) {
   if (stages < 2) return PV2_EUNSUPPORTED;
   p.stages = stages;
   const size_t smem = (size_t)stages * stage_bytes + fixed;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(umma_gather_gemm_kernel<kSplit, kPre, kGroups>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         227 * 1024);
+  {
+    static bool done[64] = {};
+    cudaError_t e = ensure_smem_optin(umma_gather_gemm_kernel<kSplit, kPre, kGroups>, done);
     if (e != cudaSuccess) return (int)e;
-    attr_set = true;
   }
   const unsigned tiles = (unsigned)((p.n_out + kTileM - 1) / kTileM);
   int ksplit = 1;
@@ -961,16 +1093,24 @@ static int fp32_groups(int cout, int kvol, int cin) {
 
 extern "C" {
 
-// The raw-operand fp32 path needs no scratch; kept in the ABI (returns 0) so callers can size a workspace uniformly.
+static int bx3_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("PV2_GG_BX3"); v = (e && e[0] == '0') ? 0 : 1; }   // development A/B switch
+  return v;
+}
+
+// fp32: room for the weights pre-split into bf16 hi / lo matrices (the bf16x3 kernel's TMA operand); bf16: none.
 size_t pv2_spconv_workspace_bytes(int64_t n_in, int cin, int cout, int kvol, int dtype) {
-  (void)n_in; (void)cin; (void)cout; (void)kvol; (void)dtype;
-  return 0;
+  (void)n_in;
+  if (dtype != PV2_F32 || cin <= 0 || cout <= 0 || kvol <= 0) return 0;
+  const size_t rows = ((size_t)cout + 15) / 16 * 16, cols = ((size_t)kvol * cin + 63) / 64 * 64;
+  return (2 * rows * cols * 2 + 255) / 256 * 256;
 }
 
 // returns PV2_EUNSUPPORTED when the shape does not fit the tensor-core kernel (caller falls back to the SIMT kernel)
 int pv2_spconv_gather_gemm_umma(const void* x, const void* w, int64_t w_sco, int64_t w_sk, const float* bias,
                                 const int32_t* nbr, const int32_t* order, void* y, int64_t n_in, int64_t n_out, int cin,
-                                int cout, int kvol, int dtype, void* stream_) {
+                                int cout, int kvol, int dtype, void* workspace, size_t workspace_bytes, void* stream_) {
   PV2_CHECK_ARG(n_in >= 0 && n_out >= 0 && cin > 0 && cout > 0 && kvol > 0);
   if (n_out == 0) return 0;
   PV2_CHECK_ARG(x && w && nbr && y);
@@ -990,12 +1130,31 @@ int pv2_spconv_gather_gemm_umma(const void* x, const void* w, int64_t w_sco, int
   const int nsl = (cout + 255) / 256;
   const int per = ((cout + nsl - 1) / nsl + 15) / 16 * 16;
   const int eb = (dtype == PV2_BF16) ? 2 : 4;
+  // bf16x3 persistent kernel: fp32 layers with whole 8-channel pieces and enough row tiles to fill the SMs (the small
+  // deep levels keep the split-K 3xTF32 kernel); needs the pre-split weight workspace
+  const int64_t tiles = (n_out + kTileM - 1) / kTileM;
+  const int w2_rows = (cout + 15) / 16 * 16, w2_cols = (kvol * cin + 63) / 64 * 64;
+  bool bx3 = dtype == PV2_F32 && bx3_enabled() && (cin % 8) == 0 && tiles * 2 > PV2_SM_COUNT && workspace != nullptr &&
+             workspace_bytes >= pv2_spconv_workspace_bytes(n_in, cin, cout, kvol, dtype) && ((uintptr_t)workspace & 127) == 0 &&
+             tensor_map_encoder() != nullptr;
+  if (bx3) {
+    const int64_t total = (int64_t)w2_rows * w2_cols;
+    presplit_weights_bf16_kernel<<<pv2_grid_for(total, 256), 256, 0, stream>>>(
+        (const float*)w, w_sco, w_sk, cout, kvol, cin, (__nv_bfloat16*)workspace, w2_rows, w2_cols);
+    pv2_note_launches(1);
+  }
   for (int co0 = 0; co0 < cout; co0 += per) {
     GGParams q = p;
     q.cout = (cout - co0 < per) ? cout - co0 : per;
     q.w = (const char*)w + (size_t)co0 * w_sco * eb;
     q.bias = bias ? bias + co0 : nullptr;
     q.y = (char*)y + (size_t)co0 * eb;
+    if (bx3) {
+      q.w2_row0 = co0; q.w2_rows = w2_rows;
+      const int rp = launch_persistent(q, stream, workspace, w2_cols);
+      if (rp == 0) continue;
+      if (rp != PV2_EUNSUPPORTED) return rp;
+    }
     if (dtype == PV2_F32) {
       const int rp = launch_persistent(q, stream);
       if (rp == 0) continue;

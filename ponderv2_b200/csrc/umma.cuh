@@ -36,6 +36,35 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 // generic-proxy writes (st.shared / cp.async) -> visible to the async proxy (tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// ---- TMA (cp.async.bulk.tensor) --------------------------------------------------------------------------
+// the barrier additionally waits for `bytes` of asynchronous-proxy transactions in its current phase
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+// 2-D tile load: box (c0 .. c0 + box0, c1 .. c1 + box1) of the tensor map -> shared memory (layout / swizzle as encoded
+// in the map), completion signalled on `bar` as transaction bytes.  Out-of-bounds elements are zero-filled.
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint32_t bar, int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+// four rows (r0..r3, any order, out-of-bounds rows zero-filled) x the box width starting at column c0 -> 4 consecutive
+// box rows in shared memory
+__device__ __forceinline__ void tma_gather4_2d(uint32_t dst, const void* tmap, uint32_t bar, int32_t c0, int32_t r0,
+                                               int32_t r1, int32_t r2, int32_t r3) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
+      : "memory");
+}
+
 // ---- cp.async (LDGSTS) ----------------------------------------------------------------------------------
 // 16-byte copy; src_bytes = 0 zero-fills the destination (used for missing neighbours / padding)
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t src_bytes) {
@@ -106,6 +135,20 @@ __device__ __forceinline__ uint64_t smem_desc_kmajor_sw128(uint32_t saddr) {
 __device__ __forceinline__ uint32_t sw128_offset(int row, int chunk16) {
   return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((chunk16 ^ (row & 7)) << 4));
 }
+// MN-major operand tile (kind::f16 only): the contraction index k runs over the ROWS of the tile.  Rows of 128 bytes
+// (64 consecutive MN elements), 8-row groups of 1024 bytes with the 128-byte swizzle, i.e. physically the same tile the
+// K-major descriptor above describes -- read "transposed".  `lbo_bytes` = distance between 64-element MN panels,
+// `sbo_bytes` = distance between 8-row k groups (canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units,
+// cute/atom/mma_traits_sm100.hpp make_umma_desc<Major::MN>).
+__device__ __forceinline__ uint64_t smem_desc_mnmajor_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 // kind::f16 (BF16 x BF16 -> F32) / kind::tf32 (TF32 x TF32 -> F32), both operands K-major, M = 128
 __host__ __device__ __forceinline__ uint32_t make_idesc(int fmt /*1 = BF16, 2 = TF32*/, int m, int n) {
   uint32_t d = 0;
@@ -115,6 +158,10 @@ __host__ __device__ __forceinline__ uint32_t make_idesc(int fmt /*1 = BF16, 2 = 
   d |= (uint32_t)(n >> 3) << 17;   // N / 8
   d |= (uint32_t)(m >> 4) << 24;   // M / 16
   return d;
+}
+// same with both operands MN-major (bits 15 / 16): the weight-gradient contraction runs over voxel rows
+__host__ __device__ __forceinline__ uint32_t make_idesc_mn(int fmt, int m, int n) {
+  return make_idesc(fmt, m, n) | (1u << 15) | (1u << 16);
 }
 
 }  // namespace pv2
