@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(kGroups * 128 + 32) umma_gather_gemm_kernel(co
   constexpr int kThreads = kProducerThreads + 32;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // dynamic smem is only guaranteed 16 B aligned: round up to 1024 (the launch reserves the slack)
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS / STS, not generic LD / ST)
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -604,7 +604,7 @@ __global__ void __launch_bounds__(kPersistThreads) umma_gather_gemm_persistent_k
   constexpr int kEPR = kBx3 ? 64 : 32;   // contraction elements per 128-byte operand row (chunk)
   constexpr int kEPP = kBx3 ? 8 : 4;     // ... per 16-byte piece
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS / STS, not generic LD / ST)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b_bytes = p.n_pad * 128;
   const int stage_bytes = (kABytes + b_bytes) * 2;
@@ -905,6 +905,244 @@ __global__ void __launch_bounds__(kPersistThreads) umma_gather_gemm_persistent_k
 }
 
 // returns PV2_EUNSUPPORTED when the shape does not fit the persistent kernel (the caller uses the one-tile kernel)
+// ===============================================================================================================
+// bf16 storage, TMA on both operands (persistent).  The gather itself is done by the copy engine:
+//   * A (activations): `cp.async.bulk.tensor.2d ... tile::gather4` -- each lane of ONE producer warp hands four row indices
+//     of the tile's neighbour list to the TMA unit, which fetches the four 128-byte channel runs [row][ci0 .. ci0 + 63]
+//     straight into the 128B-swizzled K-major stage (UTMALDG in SASS).  A missing neighbour is row index -1: out of
+//     bounds for the tensor map, which the hardware zero-fills.  32 lanes x 4 rows = the 128-row tile, one warp
+//     instruction per chunk; no thread touches the data, no registers, no proxy fences;
+//   * B (weights): one 2-D box [n_pad rows][64 channels] of the bf16 weight matrix [Cout][K * Cin] per chunk;
+//   * the stage's mbarrier counts transaction bytes (16 KB + n_pad * 128), the MMA warp waits on it.
+// Roles: warp 0 producer, warp 1 MMA issuer (kind::f16, M = 128, N = Cout), warps 2-5 metadata + epilogue exactly as in
+// the fp32 persistent kernel (double-buffered tile metadata and TMEM accumulators).  Requires Cin % 64 == 0 (a chunk never
+// straddles two kernel offsets) and contiguous [Cout][K][Cin] weights; other layers use the cp.async kernel above.
+constexpr int kTmaThreads = 6 * 32;
+
+__global__ void __launch_bounds__(kTmaThreads) umma_gather_gemm_tma_kernel(const GGParams p, int num_tiles,
+                                                                           const __grid_constant__ CUtensorMap xmap,
+                                                                           const __grid_constant__ CUtensorMap wmap) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b_bytes = p.n_pad * 128;
+  const int stage_bytes = kABytes + b_bytes;
+  const int cpk = p.cin >> 6;                      // 64-channel chunks per kernel offset
+  const PersistLayout L = persist_layout(p.kvol, p.num_chunks);
+  uint8_t* stage_base = smem;
+  uint8_t* meta_base = smem + (size_t)p.stages * stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(meta_base + 2 * L.meta_bytes);
+  uint64_t* full_bar = bars;                        // [kMaxStages]  1 arrival (+ transaction bytes)
+  uint64_t* empty_bar = bars + kMaxStages;          // [kMaxStages]  tcgen05.commit
+  uint64_t* meta_full = bars + 2 * kMaxStages;      // [2]
+  uint64_t* meta_empty = meta_full + 2;             // [2]  producer warp + MMA warp
+  uint64_t* tmem_full = meta_empty + 2;             // [2]
+  uint64_t* tmem_empty = tmem_full + 2;             // [2]  4 epilogue warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint32_t* scratch = tmem_slot + 1;
+
+  auto meta_idx = [&](int b) { return reinterpret_cast<int32_t*>(meta_base + (size_t)b * L.meta_bytes); };
+  auto meta_row = [&](int b) { return meta_idx(b) + p.kvol * kTileM; };
+  auto meta_active = [&](int b) { return reinterpret_cast<uint16_t*>(meta_row(b) + kTileM); };
+  auto meta_count = [&](int b) { return reinterpret_cast<int*>(meta_base + (size_t)b * L.meta_bytes + L.meta_bytes - 16); };
+
+  const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  auto tile_row0 = [&](int i) { return (int64_t)(num_tiles - 1 - ((int)blockIdx.x + i * (int)gridDim.x)) * kTileM; };
+
+  if (tid == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&meta_full[b]), 1);
+      mbar_init(smem_u32(&meta_empty[b]), 2);
+      mbar_init(smem_u32(&tmem_full[b]), 1);
+      mbar_init(smem_u32(&tmem_empty[b]), 4);
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&xmap);
+    tma_prefetch_desc(&wmap);
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t acc_stride = p.tmem_cols >> 1;
+
+  if (warp == 0) {
+    // ======================= producer: one warp drives the copy engine =======================
+    int gbase = 0;
+    for (int i = 0; i < my_tiles; ++i) {
+      const int b = i & 1;
+      mbar_wait(smem_u32(&meta_full[b]), (uint32_t)(i >> 1) & 1u);
+      const int n_active = *meta_count(b);
+      const int32_t* idx_s = meta_idx(b);
+      const uint16_t* active = meta_active(b);
+      for (int it = 0; it < n_active; ++it) {
+        const int g = gbase + it;
+        const int s = g % p.stages;
+        const uint32_t ph = (uint32_t)(g / p.stages) & 1u;
+        const int c = (int)active[it];
+        const int k = c / cpk;
+        const int ci0 = (c - k * cpk) << 6;
+        const int4 r4 = *reinterpret_cast<const int4*>(idx_s + k * kTileM + 4 * lane);   // rows 4 lane .. 4 lane + 3
+        mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+        const uint32_t bar = smem_u32(&full_bar[s]);
+        const uint32_t a_dst = smem_u32(stage_base + (size_t)s * stage_bytes);
+        if (lane == 0) {
+          mbar_arrive_expect_tx(bar, (uint32_t)(kABytes + b_bytes));
+          tma_load_2d(a_dst + kABytes, &wmap, bar, c << 6, p.w2_row0);
+        }
+        __syncwarp();
+        tma_gather4_2d(a_dst + (uint32_t)lane * 512u, &xmap, bar, ci0, r4.x, r4.y, r4.z, r4.w);
+      }
+      gbase += n_active;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&meta_empty[b]));
+    }
+  } else if (warp == 1) {
+    // ======================= MMA issuer =======================
+    const uint32_t idesc = make_idesc(1 /*BF16*/, kTileM, p.n_pad);
+    int gbase = 0;
+    for (int i = 0; i < my_tiles; ++i) {
+      const int b = i & 1;
+      mbar_wait(smem_u32(&meta_full[b]), (uint32_t)(i >> 1) & 1u);
+      const int n_active = *meta_count(b);
+      mbar_wait(smem_u32(&tmem_empty[b]), ((uint32_t)(i >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t acc = tmem_base + (uint32_t)b * acc_stride;
+      for (int it = 0; it < n_active; ++it) {
+        const int g = gbase + it;
+        const int s = g % p.stages;
+        const uint32_t ph = (uint32_t)(g / p.stages) & 1u;
+        mbar_wait(smem_u32(&full_bar[s]), ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint64_t da = smem_desc_kmajor_sw128(smem_u32(stage_base + (size_t)s * stage_bytes));
+          const uint64_t db = da + (uint64_t)(kABytes >> 4);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) umma_bf16(acc, da + 2 * ks, db + 2 * ks, idesc, (it | ks) != 0 ? 1u : 0u);
+          umma_commit(smem_u32(&empty_bar[s]));
+          if (it == n_active - 1) umma_commit(smem_u32(&tmem_full[b]));
+        }
+        __syncwarp();
+      }
+      if (n_active == 0 && lane == 0) mbar_arrive(smem_u32(&tmem_full[b]));
+      gbase += n_active;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&meta_empty[b]));
+    }
+    tc_fence_before();
+  } else {
+    // ======================= epilogue warps: metadata of the next tile, then drain of the current one ==========
+    const int ew = warp - 2;                           // 0..3
+    const int lg = warp & 3;                           // TMEM lane group this warp may read (hardware: warp id % 4)
+    const int et = tid - 64;                           // 0..127
+    auto prepare = [&](int j) {
+      const int b = j & 1;
+      mbar_wait(smem_u32(&meta_empty[b]), ((uint32_t)(j >> 1) & 1u) ^ 1u);
+      int32_t* idx_s = meta_idx(b);
+      int32_t* row_s = meta_row(b);
+      uint16_t* active = meta_active(b);
+      const int64_t row0 = tile_row0(j);
+      const int64_t pos = row0 + et;
+      const bool in = pos < p.n_out;
+      {
+        int32_t jr = -1;
+        if (in) jr = (p.order != nullptr) ? __ldg(&p.order[pos]) : (int32_t)pos;
+        row_s[et] = jr;
+      }
+      if (et < 4) scratch[et] = 0u;
+      for (int k0 = 0; k0 < p.kvol; k0 += 9) {
+        int32_t v[9];
+#pragma unroll
+        for (int u = 0; u < 9; ++u) {
+          const int k = k0 + u;
+          v[u] = -1;
+          if (k < p.kvol && in) v[u] = (p.nbr != nullptr) ? __ldg(&p.nbr[(int64_t)k * p.n_out + pos]) : (int32_t)pos;
+        }
+#pragma unroll
+        for (int u = 0; u < 9; ++u)
+          if (k0 + u < p.kvol) idx_s[(k0 + u) * kTileM + et] = v[u];
+      }
+      bar_sync_named(1, 128);
+      for (int k = ew; k < p.kvol; k += 4) {
+        const int32_t* r = idx_s + k * kTileM + lane;
+        const bool a = (r[0] >= 0) | (r[32] >= 0) | (r[64] >= 0) | (r[96] >= 0);
+        if (__any_sync(0xffffffffu, a) && lane == 0) atomicOr(&scratch[k >> 5], 1u << (k & 31));
+      }
+      bar_sync_named(1, 128);
+      const uint32_t km[4] = {scratch[0], scratch[1], scratch[2], scratch[3]};
+      int n_total = 0;
+      for (int c0 = 0; c0 < p.num_chunks; c0 += 128) {
+        const int c = c0 + et;
+        bool on = false;
+        if (c < p.num_chunks) { const int k = c / cpk; on = ((km[k >> 5] >> (k & 31)) & 1u) != 0; }
+        const unsigned bal = __ballot_sync(0xffffffffu, on);
+        if (lane == 0) scratch[4 + ew] = __popc(bal);
+        bar_sync_named(1, 128);
+        int before = 0, all = 0;
+#pragma unroll
+        for (int w2 = 0; w2 < 4; ++w2) { const int cnt = (int)scratch[4 + w2]; before += (w2 < ew) ? cnt : 0; all += cnt; }
+        if (on) active[n_total + before + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)c;
+        n_total += all;
+        bar_sync_named(1, 128);
+      }
+      if (et == 0) *meta_count(b) = n_total;
+      bar_sync_named(1, 128);
+      if (et == 0) mbar_arrive(smem_u32(&meta_full[b]));
+    };
+    if (my_tiles > 0) prepare(0);
+    for (int i = 0; i < my_tiles; ++i) {
+      if (i + 1 < my_tiles) prepare(i + 1);
+      const int b = i & 1;
+      mbar_wait(smem_u32(&tmem_full[b]), (uint32_t)(i >> 1) & 1u);
+      tc_fence_after();
+      const int n_active = *meta_count(b);
+      const int32_t j32 = meta_row(b)[lg * 32 + lane];
+      const int64_t j = j32;
+      const uint32_t acc = tmem_base + (uint32_t)b * acc_stride + ((uint32_t)(lg * 32) << 16);
+      for (int col0 = 0; col0 < p.n_pad; col0 += 16) {
+        uint32_t v[16];
+        if (n_active > 0) {
+          tmem_ld_x16(acc + (uint32_t)col0, v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int q = 0; q < 16; ++q) v[q] = 0u;
+        }
+        if (j32 < 0) continue;
+        float f[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          const int co = col0 + q;
+          f[q] = __uint_as_float(v[q]) + ((p.bias != nullptr && co < p.cout) ? __ldg(&p.bias[co]) : 0.f);
+        }
+        __nv_bfloat16* yr = reinterpret_cast<__nv_bfloat16*>(p.y) + j * p.y_row + col0;
+        if (col0 + 16 <= p.cout && (p.cout & 7) == 0) {
+          uint32_t pk[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * q], f[2 * q + 1]);
+            pk[q] = *reinterpret_cast<uint32_t*>(&h2);
+          }
+          *reinterpret_cast<uint4*>(yr) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(yr + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        } else {
+          for (int q = 0; q < 16 && col0 + q < p.cout; ++q) yr[q] = __float2bfloat16(f[q]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tmem_empty[b]));
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: remember it per (kernel, device)
 template <typename K>
 cudaError_t ensure_smem_optin(K kernel, bool (&done)[64]) {
@@ -993,7 +1231,7 @@ int launch_persistent(const GGParams& p0, cudaStream_t stream, const void* w2 = 
   if (p.tmem_cols > 512) return PV2_EUNSUPPORTED;
   const int stage_bytes = (kABytes + p.n_pad * 128) * 2;
   const PersistLayout L = persist_layout(p.kvol, p.num_chunks);
-  int stages = (224 * 1024 - L.fixed) / stage_bytes;
+  int stages = (227 * 1024 - L.fixed) / stage_bytes;   // 227 KB: the opt-in maximum of dynamic shared memory per CTA
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < kPersistGroups) return PV2_EUNSUPPORTED;          // groups <= stages (mbarrier parity aliasing)
   p.stages = stages;
@@ -1016,6 +1254,55 @@ int launch_persistent(const GGParams& p0, cudaStream_t stream, const void* w2 = 
     if (e != cudaSuccess) return (int)e;
     umma_gather_gemm_persistent_kernel<false><<<grid, kPersistThreads, smem, stream>>>(p, tiles, wmap);
   }
+  PV2_DONE(1);
+}
+
+
+// bf16 storage through TMA gather4.  PV2_EUNSUPPORTED -> the caller uses the cp.async kernel.
+int launch_tma_bf16(const GGParams& p0, cudaStream_t stream, int64_t n_in, const void* w_full, int cout_full) {
+  static int enabled = -1;
+  if (enabled < 0) { const char* e = getenv("PV2_GG_TMA"); enabled = (e && e[0] == '0') ? 0 : 1; }   // development A/B switch
+  if (!enabled || tensor_map_encoder() == nullptr) return PV2_EUNSUPPORTED;
+  GGParams p = p0;
+  if ((p.cin & 63) != 0 || p.nbr == nullptr || p.x_row != p.cin || p.w_sk != p.cin || p.w_sco != (int64_t)p.kvol * p.cin)
+    return PV2_EUNSUPPORTED;
+  p.n_pad = (p.cout + 15) / 16 * 16;
+  if (p.n_pad > 256 || (int64_t)p.kvol * p.cin >= (1 << 30) || n_in >= (int64_t)1 << 31) return PV2_EUNSUPPORTED;
+  p.num_chunks = p.kvol * (p.cin >> 6);
+  const int tiles = (int)((p.n_out + kTileM - 1) / kTileM);
+  p.tmem_cols = 32;
+  while ((int)p.tmem_cols < 2 * p.n_pad) p.tmem_cols <<= 1;
+  if (p.tmem_cols > 512) return PV2_EUNSUPPORTED;
+  const int stage_bytes = kABytes + p.n_pad * 128;
+  const PersistLayout L = persist_layout(p.kvol, p.num_chunks);
+  // two CTAs per SM when at least three stages fit in half of the shared memory
+  int budget = 227 * 1024;
+  if ((113 * 1024 - L.fixed) / stage_bytes >= 3) budget = 113 * 1024;
+  int stages = (budget - L.fixed) / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) return PV2_EUNSUPPORTED;
+  p.stages = stages;
+  p.ksplit = 1; p.ablate = 0;
+  const size_t smem = (size_t)stages * stage_bytes + L.fixed;
+  CUtensorMap xmap, wmap;
+  EncodeTiledFn enc = tensor_map_encoder();
+  {
+    const cuuint64_t dims[2] = {(cuuint64_t)p.cin, (cuuint64_t)n_in};
+    const cuuint64_t strides[1] = {(cuuint64_t)p.cin * 2};
+    const cuuint32_t box[2] = {64u, 1u};
+    const cuuint32_t estr[2] = {1u, 1u};
+    if (enc(&xmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(p.x), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return PV2_EUNSUPPORTED;
+  }
+  if (encode_bf16_map(&wmap, w_full, cout_full, (int64_t)p.kvol * p.cin, p.n_pad) != 0) return PV2_EUNSUPPORTED;
+  static bool done[64] = {};
+  cudaError_t e = ensure_smem_optin(umma_gather_gemm_tma_kernel, done);
+  if (e != cudaSuccess) return (int)e;
+  const int ctas = (budget < 200 * 1024) ? 2 : 1;
+  const int grid = tiles < ctas * PV2_SM_COUNT ? tiles : ctas * PV2_SM_COUNT;
+  umma_gather_gemm_tma_kernel<<<grid, kTmaThreads, smem, stream>>>(p, tiles, xmap, wmap);
   PV2_DONE(1);
 }
 
@@ -1159,6 +1446,12 @@ int pv2_spconv_gather_gemm_umma(const void* x, const void* w, int64_t w_sco, int
       const int rp = launch_persistent(q, stream);
       if (rp == 0) continue;
       if (rp != PV2_EUNSUPPORTED) return rp;
+    }
+    if (dtype == PV2_BF16 && tiles * 2 > PV2_SM_COUNT) {
+      q.w2_row0 = co0;
+      const int rt = launch_tma_bf16(q, stream, n_in, w, cout);
+      if (rt == 0) continue;
+      if (rt != PV2_EUNSUPPORTED) return rt;
     }
     const int rc = dtype == PV2_BF16 ? launch<false, false, 2>(q, stream)
                                      : (fp32_groups(q.cout, kvol, cin) == 3 ? launch<true, false, 3>(q, stream)

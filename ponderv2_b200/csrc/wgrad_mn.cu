@@ -30,7 +30,9 @@ using namespace pv2;
 constexpr int kRows = 32;            // contraction rows per stage
 constexpr int kPanelBytes = kRows * 128;   // one 64-channel panel of a stage: 32 rows x 128 B
 constexpr int kMaxStagesW = 6;
-constexpr int kThreadsW = 160;
+constexpr int kGroupsW = 3;          // producer groups of 4 warps; group g gathers stages g, g + 3, ... of the active list
+constexpr int kProducerThreadsW = kGroupsW * 128;
+constexpr int kThreadsW = kProducerThreadsW + 32;
 
 struct WMParams {
   const void* x;       // [n_in][cin]   (fp32 or bf16)
@@ -67,12 +69,12 @@ __device__ __forceinline__ void split8_store(uint32_t addr, uint32_t lo_delta, c
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr + lo_delta), "r"(lp[0]), "r"(lp[1]), "r"(lp[2]), "r"(lp[3]) : "memory");
 }
 
-// kBf16: storage type of x / dy.  Stage layout: [A_hi: a_panels x 4 KB][A_lo][B_hi: b_panels x 4 KB][B_lo] (the lo
-// halves only exist for fp32 storage).
-template <bool kBf16>
+// kBf16: storage type of x / dy.  kBP: 64-channel panels of X a thread may hold (2: Cin <= 128, 4: Cin <= 256).
+// Stage layout: [A_hi: a_panels x 4 KB][A_lo][B_hi: b_panels x 4 KB][B_lo] (the lo halves only exist for fp32 storage).
+template <bool kBf16, int kBP>
 __global__ void __launch_bounds__(kThreadsW, 1) umma_wgrad_mn_kernel(const WMParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS / STS, not generic LD / ST)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int k = blockIdx.y;
   const int co0 = blockIdx.z * 128;
@@ -131,126 +133,141 @@ __global__ void __launch_bounds__(kThreadsW, 1) umma_wgrad_mn_kernel(const WMPar
     mbar_init(smem_u32(tmem_full_bar), 1);
     fence_mbar_init();
   }
-  if (warp == 4) tmem_alloc(smem_u32(tmem_slot), p.tmem_cols);
+  if (warp == kGroupsW * 4) tmem_alloc(smem_u32(tmem_slot), p.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
+  if (warp < kGroupsW * 4) {
     // ------------------------------- producers -------------------------------
-    // work item = (row r of the stage, 16-byte bf16 piece = 8 channels); A items first, then B items.
-    const int a_ppr = p.a_panels * 8;                 // pieces per dY row held by the tile (64 or 128 channels)
-    const int b_ppr = p.n_pad >> 3;                   // pieces per X row (cin rounded to 16 -> even)
-    const int a_items = kRows * a_ppr, b_items = kRows * b_ppr;   // multiples of 128? a: 256 / 512 yes; b: 32 * {2..32}
-    constexpr int kAMax = 4, kBMax = 8;               // items per thread: 512 / 128, 1024 / 128
+    // Group g owns stages g, g + kGroupsW, ... of the active list, so up to kGroupsW stage gathers are in flight per CTA.
+    // Within a group: 8 threads per row (one 16-byte bf16 piece = 8 channels of every 64-channel panel each), 16 rows
+    // per pass, two passes -> a quarter warp stores one whole 128-byte row: conflict-free with the 128-byte swizzle.
+    // The row indices (dY row through `order`, X row through the neighbour map) are fetched one own-stage ahead.
+    const int grp = warp >> 2;
+    const int tg = tid & 127;
+    const int piece = tg & 7, rbase = tg >> 3;            // rows rbase, rbase + 16
+    const uint32_t off0 = sw128_offset(rbase, piece);      // row rbase + 16 -> + 2048
     const uint8_t* zp = reinterpret_cast<const uint8_t*>(g_zero_page_w);
-    const int eb = kBf16 ? 2 : 4;
-    // per-thread item geometry is stage-independent
-    int a_row[kAMax], a_pc[kAMax], b_row[kBMax], b_pc[kBMax];
+    constexpr int eb = kBf16 ? 2 : 4;
+    const int64_t ch_a = co0 + piece * 8;                  // + 64 per panel
+    const int ch_b = piece * 8;
+    auto fetch_idx = [&](int it, int64_t (&jrow)[2], int32_t (&src)[2]) {
 #pragma unroll
-    for (int i = 0; i < kAMax; ++i) { const int it = tid + i * 128; a_row[i] = (it < a_items) ? it / a_ppr : -1; a_pc[i] = (it < a_items) ? it - a_row[i] * a_ppr : 0; }
-#pragma unroll
-    for (int i = 0; i < kBMax; ++i) { const int it = tid + i * 128; b_row[i] = (it < b_items) ? it / b_ppr : -1; b_pc[i] = (it < b_items) ? it - b_row[i] * b_ppr : 0; }
-    auto smem_off = [](int row, int pc) -> uint32_t { return (uint32_t)((pc >> 3) * kPanelBytes) + sw128_offset(row, pc & 7); };
-
-    const int lag = kBf16 ? (p.stages >= 2 ? p.stages / 2 : 1) : 0;
-    for (int it = 0; it < n_act + lag; ++it) {
+      for (int rr = 0; rr < 2; ++rr) {
+        jrow[rr] = -1; src[rr] = -1;
+        if (it < n_act) {
+          const int64_t pos = r_begin + (int64_t)stage_at(it) * kRows + rbase + 16 * rr;
+          if (pos < r_end) {
+            jrow[rr] = (p.order != nullptr) ? (int64_t)__ldg(&p.order[pos]) : pos;
+            src[rr] = (p.nbr != nullptr) ? __ldg(&p.nbr[(int64_t)k * p.n_out + pos]) : (int32_t)pos;
+          }
+        }
+      }
+    };
+    int64_t jrow[2]; int32_t src[2];
+    fetch_idx(grp, jrow, src);
+    const int lag = kBf16 ? 1 : 0;     // own-stage iterations between issuing the copies and signalling them (cp.async)
+    int it_prev = -1;
+    for (int it = grp; it < n_act + lag * kGroupsW; it += kGroupsW) {
       if (it < n_act) {
         const int s = it % p.stages;
         const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-        const int64_t pos0 = r_begin + (int64_t)stage_at(it) * kRows;
-        uint8_t* st_base = smem + (size_t)s * stage_bytes;
-        const uint32_t a_base = smem_u32(st_base), b_base = a_base + kHalves * a_bytes;
-        // source row of every item (dY: tile position -> row through `order`; X: through the neighbour map)
-        const uint8_t* a_src[kAMax];
-        const uint8_t* b_src[kBMax];
+        const uint32_t a_base = smem_u32(smem + (size_t)s * stage_bytes), b_base = a_base + kHalves * a_bytes;
+        const uint8_t* a_src[2][2];
+        const uint8_t* b_src[2][kBP];
 #pragma unroll
-        for (int i = 0; i < kAMax; ++i) {
-          a_src[i] = zp;
-          if (a_row[i] >= 0) {
-            const int64_t pos = pos0 + a_row[i];
-            const int ch = co0 + a_pc[i] * 8;
-            if (pos < r_end && ch < p.cout) {
-              const int64_t j = (p.order != nullptr) ? (int64_t)__ldg(&p.order[pos]) : pos;
-              a_src[i] = reinterpret_cast<const uint8_t*>(p.dy) + (j * p.dy_row + ch) * eb;
-            }
+        for (int rr = 0; rr < 2; ++rr) {
+#pragma unroll
+          for (int pn = 0; pn < 2; ++pn) {
+            const int64_t ch = ch_a + 64 * pn;
+            a_src[rr][pn] = (jrow[rr] >= 0 && pn < p.a_panels && ch < p.cout)
+                                ? reinterpret_cast<const uint8_t*>(p.dy) + (jrow[rr] * p.dy_row + ch) * eb : zp;
           }
-        }
 #pragma unroll
-        for (int i = 0; i < kBMax; ++i) {
-          b_src[i] = zp;
-          if (b_row[i] >= 0) {
-            const int64_t pos = pos0 + b_row[i];
-            const int ch = b_pc[i] * 8;
-            if (pos < r_end && ch < p.cin) {
-              const int32_t src = (p.nbr != nullptr) ? __ldg(&p.nbr[(int64_t)k * p.n_out + pos]) : (int32_t)pos;
-              if (src >= 0) b_src[i] = reinterpret_cast<const uint8_t*>(p.x) + ((int64_t)src * p.x_row + ch) * eb;
-            }
+          for (int pn = 0; pn < kBP; ++pn) {
+            const int ch = ch_b + 64 * pn;
+            b_src[rr][pn] = (src[rr] >= 0 && ch < p.cin)
+                                ? reinterpret_cast<const uint8_t*>(p.x) + ((int64_t)src[rr] * p.x_row + ch) * eb : zp;
           }
         }
         if constexpr (kBf16) {
+          fetch_idx(it + kGroupsW, jrow, src);            // next own stage's indices, in flight across the wait
           mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
 #pragma unroll
-          for (int i = 0; i < kAMax; ++i)
-            if (a_row[i] >= 0) cp_async_16(a_base + smem_off(a_row[i], a_pc[i]), a_src[i], a_src[i] != zp ? 16u : 0u);
+          for (int rr = 0; rr < 2; ++rr) {
 #pragma unroll
-          for (int i = 0; i < kBMax; ++i)
-            if (b_row[i] >= 0) cp_async_16(b_base + smem_off(b_row[i], b_pc[i]), b_src[i], b_src[i] != zp ? 16u : 0u);
+            for (int pn = 0; pn < 2; ++pn)
+              if (pn < p.a_panels)
+                cp_async_16(a_base + pn * kPanelBytes + off0 + rr * 2048, a_src[rr][pn], a_src[rr][pn] != zp ? 16u : 0u);
+#pragma unroll
+            for (int pn = 0; pn < kBP; ++pn)
+              if (pn < p.b_panels && ch_b + 64 * pn < p.n_pad)
+                cp_async_16(b_base + pn * kPanelBytes + off0 + rr * 2048, b_src[rr][pn], b_src[rr][pn] != zp ? 16u : 0u);
+          }
         } else {
-          float4 va[kAMax][2], vb[kBMax][2];
+          float4 va[2][2][2], vb[2][kBP][2];
 #pragma unroll
-          for (int i = 0; i < kAMax; ++i) {
-            va[i][0] = __ldg(reinterpret_cast<const float4*>(a_src[i]));
-            va[i][1] = __ldg(reinterpret_cast<const float4*>(a_src[i]) + 1);
-          }
+          for (int rr = 0; rr < 2; ++rr) {
 #pragma unroll
-          for (int i = 0; i < kBMax; ++i) {
-            vb[i][0] = __ldg(reinterpret_cast<const float4*>(b_src[i]));
-            vb[i][1] = __ldg(reinterpret_cast<const float4*>(b_src[i]) + 1);
+            for (int pn = 0; pn < 2; ++pn) {
+              va[rr][pn][0] = __ldg(reinterpret_cast<const float4*>(a_src[rr][pn]));
+              va[rr][pn][1] = __ldg(reinterpret_cast<const float4*>(a_src[rr][pn]) + 1);
+            }
+#pragma unroll
+            for (int pn = 0; pn < kBP; ++pn) {
+              vb[rr][pn][0] = __ldg(reinterpret_cast<const float4*>(b_src[rr][pn]));
+              vb[rr][pn][1] = __ldg(reinterpret_cast<const float4*>(b_src[rr][pn]) + 1);
+            }
           }
+          fetch_idx(it + kGroupsW, jrow, src);            // next own stage's indices, in flight across the wait
           mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
 #pragma unroll
-          for (int i = 0; i < kAMax; ++i)
-            if (a_row[i] >= 0) split8_store(a_base + smem_off(a_row[i], a_pc[i]), (uint32_t)a_bytes, va[i][0], va[i][1]);
+          for (int rr = 0; rr < 2; ++rr) {
 #pragma unroll
-          for (int i = 0; i < kBMax; ++i)
-            if (b_row[i] >= 0) split8_store(b_base + smem_off(b_row[i], b_pc[i]), (uint32_t)b_bytes, vb[i][0], vb[i][1]);
+            for (int pn = 0; pn < 2; ++pn)
+              if (pn < p.a_panels)
+                split8_store(a_base + pn * kPanelBytes + off0 + rr * 2048, (uint32_t)a_bytes, va[rr][pn][0], va[rr][pn][1]);
+#pragma unroll
+            for (int pn = 0; pn < kBP; ++pn)
+              if (pn < p.b_panels && ch_b + 64 * pn < p.n_pad)
+                split8_store(b_base + pn * kPanelBytes + off0 + rr * 2048, (uint32_t)b_bytes, vb[rr][pn][0], vb[rr][pn][1]);
+          }
           fence_proxy_async_smem();
           mbar_arrive(smem_u32(&full_bar[s]));
         }
       }
       if constexpr (kBf16) {
         cp_async_commit();
-        if (it >= lag) {
-          switch (lag) {
-            case 1: cp_async_wait<1>(); break;
-            case 2: cp_async_wait<2>(); break;
-            default: cp_async_wait<3>(); break;
-          }
+        if (it_prev >= 0) {
+          cp_async_wait<1>();                              // the previous own stage's copies have landed
           fence_proxy_async_smem();
-          mbar_arrive(smem_u32(&full_bar[(it - lag) % p.stages]));
+          mbar_arrive(smem_u32(&full_bar[it_prev % p.stages]));
         }
+        it_prev = (it < n_act) ? it : -1;
       }
     }
-    // ------------------------------- epilogue -------------------------------
-    mbar_wait(smem_u32(tmem_full_bar), 0);
-    tc_fence_after();
-    const int co = co0 + warp * 32 + lane;
-    for (int col0 = 0; col0 < p.n_pad; col0 += 16) {
-      uint32_t v[16];
-      tmem_ld_x16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)col0, v);
-      tmem_ld_wait();
-      if (co >= p.cout) continue;
-      float* dst = p.dw + ((int64_t)co * p.kvol + k) * p.dw_row + col0;
-      if (col0 + 16 <= p.cin && (p.dw_row & 3) == 0) {
+    // ------------------------------- epilogue (warps 0-3: TMEM lanes 32 w .. 32 w + 31) -------------------------------
+    if (warp < 4) {
+      mbar_wait(smem_u32(tmem_full_bar), 0);
+      tc_fence_after();
+      const int co = co0 + warp * 32 + lane;
+      for (int col0 = 0; col0 < p.n_pad; col0 += 16) {
+        uint32_t v[16];
+        tmem_ld_x16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)col0, v);
+        tmem_ld_wait();
+        if (co >= p.cout) continue;
+        float* dst = p.dw + ((int64_t)co * p.kvol + k) * p.dw_row + col0;
+        if (col0 + 16 <= p.cin && (p.dw_row & 3) == 0) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * q), "f"(__uint_as_float(v[4 * q])),
-                       "f"(__uint_as_float(v[4 * q + 1])), "f"(__uint_as_float(v[4 * q + 2])),
-                       "f"(__uint_as_float(v[4 * q + 3])) : "memory");
-      } else {
-        for (int i = 0; i < 16 && col0 + i < p.cin; ++i) atomicAdd(dst + i, __uint_as_float(v[i]));
+          for (int q = 0; q < 4; ++q)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * q), "f"(__uint_as_float(v[4 * q])),
+                         "f"(__uint_as_float(v[4 * q + 1])), "f"(__uint_as_float(v[4 * q + 2])),
+                         "f"(__uint_as_float(v[4 * q + 3])) : "memory");
+        } else {
+          for (int i = 0; i < 16 && col0 + i < p.cin; ++i) atomicAdd(dst + i, __uint_as_float(v[i]));
+        }
       }
     }
     tc_fence_before();
@@ -288,13 +305,13 @@ __global__ void __launch_bounds__(kThreadsW, 1) umma_wgrad_mn_kernel(const WMPar
     tc_fence_before();
   }
   __syncthreads();
-  if (warp == 4) {
+  if (warp == kGroupsW * 4) {
     tc_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
   }
 }
 
-template <bool kBf16>
+template <bool kBf16, int kBP>
 int launch_wgrad_mn(WMParams p, cudaStream_t stream) {
   p.n_pad = (p.cin + 15) / 16 * 16;
   p.b_panels = (p.n_pad + 63) / 64;
@@ -305,8 +322,8 @@ int launch_wgrad_mn(WMParams p, cudaStream_t stream) {
   constexpr int kHalves = kBf16 ? 1 : 2;
   const int stage_bytes = kHalves * (p.a_panels + p.b_panels) * kPanelBytes;
   const int m_tiles = (p.cout + 127) / 128;
-  // ~2 CTAs per SM in total, chunks of at least 512 rows
-  int64_t chunks = (2LL * PV2_SM_COUNT + (int64_t)p.kvol * m_tiles - 1) / ((int64_t)p.kvol * m_tiles);
+  // ~3 waves of one CTA per SM (the CTAs of different offsets differ a lot in active blocks), chunks of >= 512 rows
+  int64_t chunks = (3LL * PV2_SM_COUNT + (int64_t)p.kvol * m_tiles - 1) / ((int64_t)p.kvol * m_tiles);
   const int64_t max_chunks = (p.n_out + 511) / 512;
   if (chunks > max_chunks) chunks = max_chunks;
   if (chunks < 1) chunks = 1;
@@ -317,10 +334,10 @@ int launch_wgrad_mn(WMParams p, cudaStream_t stream) {
   p.max_iters = (int)(p.rows_per_chunk / kRows);
   // + one panel the M = 128 MMA may read past a one-panel A tile of the last stage
   const int fixed = (2 * kMaxStagesW + 2) * 8 + 64 + 1024 + 3 * p.max_iters + 16 + kPanelBytes;
-  int stages = (100 * 1024 - fixed) / stage_bytes;       // two CTAs per SM when they fit
-  if (stages < 3) stages = (220 * 1024 - fixed) / stage_bytes;
+  int stages = (220 * 1024 - fixed) / stage_bytes;
   if (stages > kMaxStagesW) stages = kMaxStagesW;
-  if (stages < 2) return PV2_EUNSUPPORTED;
+  // a group may only wait one phase ahead on a stage's mbarrier (parity waits alias every second phase): groups <= stages
+  if (stages < kGroupsW) return PV2_EUNSUPPORTED;
   p.stages = stages;
   static bool done[64] = {};
   {
@@ -328,14 +345,14 @@ int launch_wgrad_mn(WMParams p, cudaStream_t stream) {
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return (int)e;
     if (dev < 0 || dev >= 64 || !done[dev]) {
-      e = cudaFuncSetAttribute(umma_wgrad_mn_kernel<kBf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      e = cudaFuncSetAttribute(umma_wgrad_mn_kernel<kBf16, kBP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       if (e != cudaSuccess) return (int)e;
       if (dev >= 0 && dev < 64) done[dev] = true;
     }
   }
   const size_t smem = (size_t)stages * stage_bytes + fixed;
   dim3 grid((unsigned)chunks, (unsigned)p.kvol, (unsigned)m_tiles);
-  umma_wgrad_mn_kernel<kBf16><<<grid, kThreadsW, smem, stream>>>(p);
+  umma_wgrad_mn_kernel<kBf16, kBP><<<grid, kThreadsW, smem, stream>>>(p);
   PV2_DONE(1);
 }
 
@@ -369,7 +386,9 @@ int pv2_wgrad_mn(const void* x, const void* dy, const int32_t* nbr, const int32_
     q.cin = (cin - ci0 < per) ? cin - ci0 : per;
     q.x = (const char*)x + (size_t)ci0 * eb;
     q.dw = dw + ci0;
-    const int rc = dtype == PV2_BF16 ? launch_wgrad_mn<true>(q, stream) : launch_wgrad_mn<false>(q, stream);
+    const bool wide = q.cin > 128;
+    const int rc = dtype == PV2_BF16 ? (wide ? launch_wgrad_mn<true, 4>(q, stream) : launch_wgrad_mn<true, 2>(q, stream))
+                                     : (wide ? launch_wgrad_mn<false, 4>(q, stream) : launch_wgrad_mn<false, 2>(q, stream));
     if (rc != 0) return rc;
   }
   return 0;

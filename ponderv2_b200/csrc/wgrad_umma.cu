@@ -62,7 +62,7 @@ __device__ __forceinline__ void split_tf32_dev(float v, float& hi, float& lo) {
 template <bool kPre, int kUnits>
 __global__ void __launch_bounds__(kThreads, kUnits == 8 ? 2 : 1) umma_wgrad_kernel(const WGParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS / STS, not generic LD / ST)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int k = blockIdx.y;
   const int co0 = blockIdx.z * 128;

@@ -1,4 +1,6 @@
 """One pretraining step of the hot path: SpUNet backbone -> densify -> dense projection -> NeuS renderer -> losses.
+`PonderIndoorStep` mirrors PonderIndoor (below), `PonderOutdoorStep` mirrors PonderOutdoor
+(ponder_outdoor_base.py:18-265: masking :93-139, prepare_ray :141-176, to_dense :178-210, render_func :218-251).
 
 Host-side mirror of `PonderIndoor.forward` (ponder_indoor_base.py:694-706) with its `extract_feature` (:120-175,
 masking off as in the shipped indoor configs), `prepare_volume` (:635-640), `render_func` (:642-674) and `render_loss`
@@ -63,8 +65,10 @@ class _SceneViews(torch.autograd.Function):
 
 class PonderIndoorStep(nn.Module):
     def __init__(self, backbone: dict, renderer: dict, projection: Optional[dict] = None,
-                 grid_shape: Sequence[int] = (128, 128, 32), grid_size: float = 0.02, pool_type: str = "mean"):
+                 grid_shape: Sequence[int] = (128, 128, 32), grid_size: float = 0.02, pool_type: str = "mean",
+                 val_ray_split: int = 10240):
         super().__init__()
+        self.val_ray_split = int(val_ray_split)
         if pool_type != "mean":
             raise NotImplementedError("pool_type: every shipped config uses 'mean'")
         bb = dict(backbone); bb.pop("type", None)
@@ -93,9 +97,112 @@ class PonderIndoorStep(nn.Module):
         outs = []
         scene_vols = _SceneViews.apply(volume)
         for i in range(data_dict["ray_o"].shape[0]):                # scenes are independent (render_func :645-669)
-            rb = RayBundle(origins=data_dict["ray_o"][i], directions=data_dict["ray_d"][i])
-            outs.append(self.renderer(rb, [scene_vols[i]], noise=noise))
+            o, d = data_dict["ray_o"][i], data_dict["ray_d"][i]
+            if self.training:
+                outs.append(self.renderer(RayBundle(origins=o, directions=d), [scene_vols[i]], noise=noise))
+            else:   # eval: rays in chunks of val_ray_split, outputs detached (ponder_indoor_base.py:655-668)
+                parts = [self.renderer(RayBundle(origins=oo, directions=dd), [scene_vols[i]], noise=noise)
+                         for oo, dd in zip(o.split(self.val_ray_split), d.split(self.val_ray_split))]
+                outs.append({k: torch.cat([q[k].detach() for q in parts], 0) for k in parts[0]})
         render_out = outs[0] if len(outs) == 1 else {k: torch.cat([o[k] for o in outs], dim=0) for k in outs[0]}
         loss_dict = self.renderer.get_loss(render_out, {"depth": data_dict["depth"], "rgb": data_dict.get("rgb")})
+        loss = sum(v for k, v in loss_dict.items() if "loss" in k)
+        return dict(loss=loss, **loss_dict)
+
+
+class PonderOutdoorStep(nn.Module):
+    """`PonderOutdoor.forward` (ponder_outdoor_base.py:258-265) on the B200 kernels, single-dataset form (the shipped
+    nuScenes / Waymo / SemanticKITTI base configs list one condition each; `scene_bbox`, `grid_shape`, `grid_size` are
+    that condition's entries).  data_dict: grid_coord [N,3] int64, coord [N,3] f32 (metres, sensor frame), feat [N,4],
+    offset [B], ray_start / ray_end [sum R,3], ray_offset [B] (cumulative)."""
+
+    def __init__(self, backbone: dict, renderer: dict, projection: Optional[dict] = None, mask: Optional[dict] = None,
+                 scene_bbox: Sequence[float] = (-54.0, -54.0, -5.0, 54.0, 54.0, 3.0),
+                 grid_shape: Sequence[int] = (180, 180, 5), grid_size: Sequence[float] = (0.6, 0.6, 1.6),
+                 val_ray_split: int = 8192, pool_type: str = "mean"):
+        super().__init__()
+        if pool_type != "mean":
+            raise NotImplementedError("pool_type: every shipped config uses 'mean'")
+        bb = dict(backbone); bb.pop("type", None)
+        self.backbone = SpUNetBase(**bb)
+        proj = dict(projection or dict(in_channels=96, out_channels=32)); proj.pop("type", None)
+        self.proj_net = SimpleConv3D(**proj).to(memory_format=torch.channels_last_3d)
+        self.renderer = build_renderer(renderer)
+        self.scene_bbox = tuple(float(v) for v in scene_bbox)
+        self.grid_shape = tuple(int(g) for g in grid_shape)
+        self.grid_size = tuple(float(g) for g in grid_size)
+        self.val_ray_split = int(val_ray_split)
+        self.mask = dict(mask) if mask is not None else None
+        if self.mask is not None:
+            tok = nn.Parameter(torch.zeros(1, int(self.mask["channel"])))
+            nn.init.trunc_normal_(tok, mean=0.0, std=0.02, a=-0.02, b=0.02)
+            self.register_parameter("mtoken", tok)
+
+    # -- extract_feature (:93-139): random block masking of the input features, then the backbone
+    def mask_features(self, grid_coord, feat, offset, noise: Optional[torch.Tensor] = None):
+        """Blocks of `mask.size`^3 voxels; per scene a uniformly random subset of round(n_blocks * (1 - ratio)) blocks is
+        kept, every voxel of the other blocks gets the learned `mtoken`.  `noise` [n_blocks] replaces the random keys
+        (tests).  One host sync (torch.unique's output size), against one per scene in the reference."""
+        n = grid_coord.shape[0]
+        batch = torch.searchsorted(offset, torch.arange(n, device=offset.device), right=True)
+        blk = torch.cat([batch[:, None], torch.div(grid_coord, int(self.mask["size"]), rounding_mode="floor")], -1)
+        ublk, inv = blk.unique(return_inverse=True, dim=0)
+        nb = ublk.shape[0]
+        scene = ublk[:, 0]
+        key = noise if noise is not None else torch.rand(nb, device=feat.device)
+        order = torch.argsort(scene.double() * 2.0 + key.double())         # scenes stay together, random inside
+        rank = torch.empty_like(order)
+        rank[order] = torch.arange(nb, device=order.device)
+        per_scene = torch.bincount(scene, minlength=int(offset.shape[0]))
+        start = torch.cumsum(per_scene, 0) - per_scene
+        keep_n = torch.round(per_scene.double() * (1.0 - float(self.mask["ratio"]))).long()
+        keep = (rank - start[scene]) < keep_n[scene]
+        voxel_keep = keep[inv]
+        return torch.where(voxel_keep[:, None], feat, self.mtoken.to(feat.dtype).expand_as(feat))
+
+    # -- prepare_ray (:141-176)
+    @torch.no_grad()
+    def prepare_ray(self, data_dict):
+        bb = torch.tensor(self.scene_bbox, dtype=data_dict["ray_start"].dtype, device=data_dict["ray_start"].device)
+        norm = lambda c: (c - bb[:3]) / (bb[3:] - bb[:3])
+        o, e = norm(data_dict["ray_start"]), norm(data_dict["ray_end"])
+        rd = dict(ray_offset=data_dict["ray_offset"], ray_o=o, ray_d=torch.nn.functional.normalize(e - o, dim=-1),
+                  depth=torch.linalg.norm(e - o, dim=-1, keepdim=True))
+        if "ray_color" in data_dict:
+            rd["rgb"] = data_dict["ray_color"]
+        return rd
+
+    # -- to_dense (:178-210)
+    def to_dense(self, data_dict) -> torch.Tensor:
+        offset = data_dict["offset"]
+        n = data_dict["coord"].shape[0]
+        batch = torch.searchsorted(offset, torch.arange(n, device=offset.device), right=True)
+        cell = densify.outdoor_cells(data_dict["coord"], batch, self.scene_bbox, self.grid_size, self.grid_shape)
+        X, Y, Z = self.grid_shape
+        return densify.scatter_mean_volume(data_dict["sparse_backbone_feat"], cell, int(offset.shape[0]), (Z, Y, X))
+
+    def forward(self, data_dict: Dict[str, torch.Tensor], noise: Optional[dict] = None) -> Dict[str, torch.Tensor]:
+        noise = noise or {}
+        if self.mask is not None:
+            data_dict = dict(data_dict)
+            data_dict["feat"] = self.mask_features(data_dict["grid_coord"], data_dict["feat"], data_dict["offset"],
+                                                   noise.get("mask"))
+        data_dict["sparse_backbone_feat"] = self.backbone(data_dict)
+        ray = self.prepare_ray(data_dict)
+        volume = self.proj_net(self.to_dense(data_dict))
+        scene_vols = _SceneViews.apply(volume)
+        ro = ray["ray_offset"]
+        bounds = [0] + [int(v) for v in (ro.tolist() if torch.is_tensor(ro) else ro)]
+        outs = []
+        for i in range(len(bounds) - 1):                               # render_func (:218-251)
+            o, d = ray["ray_o"][bounds[i]:bounds[i + 1]], ray["ray_d"][bounds[i]:bounds[i + 1]]
+            if self.training:
+                outs.append(self.renderer(RayBundle(origins=o, directions=d), [scene_vols[i]], noise=noise))
+            else:
+                parts = [self.renderer(RayBundle(origins=oo, directions=dd), [scene_vols[i]], noise=noise)
+                         for oo, dd in zip(o.split(self.val_ray_split), d.split(self.val_ray_split))]
+                outs.append({k: torch.cat([q[k].detach() for q in parts], 0) for k in parts[0]})
+        render_out = outs[0] if len(outs) == 1 else {k: torch.cat([q[k] for q in outs], dim=0) for k in outs[0]}
+        loss_dict = self.renderer.get_loss(render_out, {"depth": ray["depth"], "rgb": ray.get("rgb")})
         loss = sum(v for k, v in loss_dict.items() if "loss" in k)
         return dict(loss=loss, **loss_dict)
