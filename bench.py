@@ -1,22 +1,29 @@
 """Benchmark of the PonderV2 pretraining hot path on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c1]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c4|c1]
 
 One "step" = one full pretraining iteration on one synthetic scene per GPU: SpUNet backbone forward/backward (rulebooks
 rebuilt every step), densify, dense projection, NeuS render of R rays x S samples with its second-order backward,
-the losses, the single gradient all-reduce (N > 1) and the optimizer step.  Prints ONE JSON line on rank 0.
+the losses, the gradient all-reduce (N > 1; slices overlapped with backward) and the optimizer step.  Prints ONE JSON
+line on rank 0.  Three separate timed loops (the same K steps each, barrier + synchronize on both sides):
 
-  value    rays/s with inputs resident in HBM (device-timed, CUDA events, max over ranks)
+  value    rays/s with inputs resident in HBM, NO per-call instrumentation (device-timed, CUDA events, max over ranks)
   e2e      same metric through the host-facing call: inputs in pinned host memory, H2D inside the timed region,
            loss read back (D2H) every step
-  roofline dominant hand-written kernel family (sparse-conv gather-GEMM, forward + data gradient of all 59 layers):
-           algorithmic bytes / CUDA-event time, summed over its launches inside the timed region, vs the measured copy
+  roofline third loop with one CUDA-event pair around every sparse-conv C-ABI call: dominant hand-written kernel family
+           (gather-GEMM, forward + data gradient of all 59 layers): algorithmic bytes / event time vs the measured copy
            bandwidth in MEASURED_PEAKS.json; `traffic` = DRAM bytes per launch from the newest committed ncu launch list
            (profiles/*_traffic.json, written by tools/traffic_from_launches.py)
-  cpu_baseline  the CPU oracle (port of the reference path) timed on the host cores on a bounded sample
+  cpu_baseline  the CPU oracle (port of the reference path: backbone + densify + projection + renderer + SGD update)
+           timed on the host cores on a bounded sample, extrapolated linearly; the sample and both numbers are stated
+
+Workloads (BASELINE.json configs): c2 = configs[1] (default: the single-GPU configuration the metric is quoted on),
+c3 = configs[2] (200 k voxels, 8192 rays, bf16 autocast backbone), c4 = configs[3] (outdoor, 80 k voxels, 2048 rays x
+(192 + 64) samples), c1 = configs[0] (plumbing size).
 
 `--impl reference` times the reference's own algorithm on the CPU (oracle port: spconv is not installable offline and
-smooth_sampler is CUDA-only) with every host thread, on a bounded sample of the same workload.
+smooth_sampler is CUDA-only) with every host thread; each step is a bounded sample of the workload sized
+from a calibration step so that the whole run stays within a few minutes.
 """
 from __future__ import annotations
 
@@ -44,7 +51,16 @@ WORKLOADS = {
     # BASELINE.json configs[0]: plumbing-size case
     "c1": dict(name="synthetic 1 scene, 2k voxels, 128 rays x 32 samples (24+8), fp32",
                voxels=2_000, rays=128, s0=24, si=8, grid_shape=(32, 32, 16), cfg_id=1),
+    # BASELINE.json configs[2]: Structured3D-shape, ~200 k voxels, 8192 rays x 128, bf16 (reference: fp16 autocast), DDP
+    "c3": dict(name="Structured3D-shape synthetic: 200k voxels SpUNet-v1m1, 8192 rays x 128 samples (96+32), bf16 autocast",
+               voxels=200_000, rays=8192, s0=96, si=32, grid_shape=(128, 128, 32), cfg_id=3, dtype="bf16"),
+    # BASELINE.json configs[3]: nuScenes-shape outdoor, ~80 k voxels over 108 x 108 x 8 m, 2048 rays x 256 samples
+    "c4": dict(name="nuScenes-shape synthetic outdoor: 80k voxels, 2048 rays x 256 samples (192+64), fp32",
+               voxels=80_000, rays=2048, s0=192, si=64, grid_shape=(180, 180, 5), cfg_id=4, outdoor=True),
 }
+for _w in WORKLOADS.values():
+    _w.setdefault("dtype", "f32")
+    _w.setdefault("outdoor", False)
 
 
 def renderer_cfg(s0: int, si: int) -> dict:
@@ -64,9 +80,37 @@ def renderer_cfg(s0: int, si: int) -> dict:
                                semantic_loss=0.0)))
 
 
+def outdoor_renderer_cfg(s0: int, si: int) -> dict:
+    """configs/nuscenes/pretrain-ponder-spunet-v1m1-0-base.py:31-74."""
+    return dict(
+        type="NeuSModel",
+        field=dict(type="SDFField", sdf_decoder=dict(in_dim=32, out_dim=17, hidden_size=16, n_blocks=5),
+                   beta_init=0.3, use_gradient=True, volume_type="default", padding_mode="zeros", share_volume=True),
+        collider=dict(type="AABBBoxCollider", near_plane=0.01, bbox=[0.0, 0.0, 0.0, 1.0, 1.0, 1.0]),
+        sampler=dict(type="NeuSSampler", initial_sampler="UniformSampler", num_samples=s0, num_samples_importance=si,
+                     num_upsample_steps=1, train_stratified=True, single_jitter=False),
+        loss=dict(sensor_depth_truncation=0.01, weights=dict(depth_loss=10.0)))
+
+
+OUTDOOR_BBOX = (-54.0, -54.0, -5.0, 54.0, 54.0, 3.0)
+
+
 def make_scene(wl: dict, seed: int) -> dict:
     """Host (numpy) scene: voxel cloud + ray batch, in the layout the dataloader/collate hands to the model."""
     from ponderv2_b200 import synth
+    if wl["outdoor"]:
+        c = synth.outdoor_cloud(wl["voxels"], seed)
+        rng = np.random.default_rng(seed + 7)
+        R = wl["rays"]
+        lo, hi = np.array(OUTDOOR_BBOX[:3]), np.array(OUTDOOR_BBOX[3:])
+        # lidar-like rays: from the sensor (scene centre, 1.8 m above the bbox floor) to points 5-50 m away
+        start = np.tile((lo + hi) / 2 + np.array([0.0, 0.0, -2.2]), (R, 1))
+        th, rr = rng.random(R) * 2 * np.pi, rng.uniform(5.0, 50.0, R)
+        end = start + np.stack([rr * np.cos(th), rr * np.sin(th), rng.uniform(-1.5, 2.0, R)], 1)
+        coord = c["coord"] + lo.astype(np.float32)          # sensor frame: metres inside the scene bbox
+        return dict(grid_coord=c["grid_coord"], coord=coord.astype(np.float32), feat=c["feat"], offset=c["offset"],
+                    ray_start=start.astype(np.float32), ray_end=end.astype(np.float32),
+                    ray_offset=np.array([R], dtype=np.int64))
     c = synth.indoor_cloud(wl["voxels"], seed)
     r = synth.ray_batch(wl["rays"], seed + 7)
     gc = c["grid_coord"]
@@ -164,9 +208,12 @@ def measured_peaks() -> dict:
 
 
 # ------------------------------------------------------------------------------------------------------------
-def cpu_oracle_step(wl: dict, sample_voxels: int, sample_rays: int, threads: int) -> dict:
-    """Times the CPU oracle (port of the reference path) forward+backward on a bounded sample; returns seconds and
-    the extrapolated whole-step time for the full workload (linear in voxels and in rays)."""
+def cpu_oracle_step(wl: dict, frac: float, threads: int) -> dict:
+    """Times the CPU oracle (port of the reference path) on a bounded sample of the workload: `frac` of the voxels, of the
+    rays and of the dense volume's Z extent.  Stages: SpUNet forward+backward, densify, Conv3d+BN+ReLU projection
+    forward+backward (torch CPU), NeuS render forward+backward (second order), one SGD update of every parameter.
+    Returns the seconds of each stage and the whole-step time extrapolated linearly to the full workload."""
+    from oracle import densify_oracle as do
     from oracle import spconv_oracle as so
     from oracle.render_oracle import NeusOracle, RenderConfig
     from ponderv2_b200 import synth
@@ -175,35 +222,75 @@ def cpu_oracle_step(wl: dict, sample_voxels: int, sample_rays: int, threads: int
 
     torch.set_num_threads(threads)
     torch.manual_seed(0)
-    cloud = synth.indoor_cloud(sample_voxels, 4242)
-    bb = SpUNetBase(in_channels=6, num_classes=0)
+    outdoor = wl["outdoor"]
+    sv = max(int(wl["voxels"] * frac), 1000)
+    sr = max(int(wl["rays"] * frac), 16)
+    X, Y, Z = wl["grid_shape"]
+    zs = max(int(round(Z * frac)), 2) if not outdoor else Z
+    ys = Y if not outdoor else max(int(round(Y * frac)), 4)
+    cloud = (synth.outdoor_cloud if outdoor else synth.indoor_cloud)(sv, 4242)
+    bb = SpUNetBase(in_channels=cloud["feat"].shape[1], num_classes=0)
     sd = {k: v.detach().clone().requires_grad_(v.is_floating_point() and v.dim() > 0 and "running" not in k)
           for k, v in bb.state_dict().items()}
     t0 = time.perf_counter()
     feats = so.spunet_forward(sd, cloud["grid_coord"], torch.from_numpy(cloud["feat"]), cloud["offset"])
-    feats.square().mean().backward()
-    t_bb = time.perf_counter() - t0
+    t_fwd = time.perf_counter() - t0
+    # densify + projection on the sampled slab of the dense grid
+    t0 = time.perf_counter()
+    cproj = 32 if outdoor else 128
+    cell = torch.randint(0, zs * ys * X, (sv,))
+    vol = torch.zeros(zs * ys * X, feats.shape[1]).index_add_(0, cell, feats.float())
+    cnt = torch.zeros(zs * ys * X).index_add_(0, cell, torch.ones(sv)).clamp(min=1)
+    vol = (vol / cnt[:, None]).view(1, zs, ys, X, -1).permute(0, 4, 1, 2, 3)
+    conv = torch.nn.Conv3d(96, cproj, 3, padding=1)
+    bn = torch.nn.BatchNorm3d(cproj)
+    vol_p = torch.relu(bn(conv(vol)))
+    t_proj_fwd = time.perf_counter() - t0
 
-    rcfg = renderer_cfg(wl["s0"], wl["si"])
+    rcfg = outdoor_renderer_cfg(wl["s0"], wl["si"]) if outdoor else renderer_cfg(wl["s0"], wl["si"])
     rm = build_renderer(rcfg)
     rsd = {k: v.detach().clone().requires_grad_(v.requires_grad) for k, v in rm.state_dict().items()}
     for k, p in rm.named_parameters():
         rsd[k].requires_grad_(p.requires_grad)
-    cfg = RenderConfig(bbox=[-0.55] * 3 + [0.55] * 3, near_plane=0.01, num_samples=wl["s0"],
-                       num_samples_importance=wl["si"], share_volume=False, norm_pts=True, norm_padding=0.1,
-                       loss_weights=rcfg["loss"]["weights"])
-    X, Y, Z = wl["grid_shape"]
-    vol = torch.randn(128, Z, Y, X).requires_grad_(True)
-    rays = synth.ray_batch(sample_rays, 99)
-    noise = {"uniform": torch.rand(sample_rays, wl["s0"] + 1), "pdf": torch.rand(sample_rays, wl["si"] + 1)}
+    if outdoor:
+        cfg = RenderConfig(bbox=[0, 0, 0, 1, 1, 1], near_plane=0.01, num_samples=wl["s0"], num_samples_importance=wl["si"],
+                           share_volume=True, norm_pts=False, norm_padding=0.0, sdf_points_factor=1.0, has_rgb=False,
+                           loss_weights=rcfg["loss"]["weights"], sensor_depth_truncation=0.01)
+        rays = synth.ray_batch(sr, 99, bbox=(0, 0, 0, 1, 1, 1))
+    else:
+        cfg = RenderConfig(bbox=[-0.55] * 3 + [0.55] * 3, near_plane=0.01, num_samples=wl["s0"],
+                           num_samples_importance=wl["si"], share_volume=False, norm_pts=True, norm_padding=0.1,
+                           loss_weights=rcfg["loss"]["weights"])
+        rays = synth.ray_batch(sr, 99)
+    noise = {"uniform": torch.rand(sr, wl["s0"] + 1), "pdf": torch.rand(sr, wl["si"] + 1)}
     orc = NeusOracle(rsd, cfg)
     t0 = time.perf_counter()
-    out = orc.render(torch.from_numpy(rays["rays_o"]), torch.from_numpy(rays["rays_d"]), [vol], noise, True)
-    ld = orc.loss(out, torch.from_numpy(rays["depth"]), torch.from_numpy(rays["rgb"]))
-    orc.total_loss(ld).backward()
-    t_r = time.perf_counter() - t0
-    full = t_bb * wl["voxels"] / sample_voxels + t_r * wl["rays"] / sample_rays
-    return dict(backbone_s=t_bb, render_s=t_r, full_step_s=full)
+    out = orc.render(torch.from_numpy(rays["rays_o"]), torch.from_numpy(rays["rays_d"]), [vol_p[0]], noise, True)
+    ld = orc.loss(out, torch.from_numpy(rays["depth"]), None if outdoor else torch.from_numpy(rays["rgb"]))
+    loss = orc.total_loss(ld)
+    t_r_fwd = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    loss.backward()                 # renderer (2nd order) -> projection -> densify -> backbone, one graph
+    t_bwd = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    with torch.no_grad():           # SGD(momentum, weight decay) over every parameter of the step
+        for t in list(sd.values()) + list(rsd.values()) + list(conv.parameters()) + list(bn.parameters()):
+            if t.grad is not None:
+                buf = t.grad + 1e-4 * t
+                t.add_(buf, alpha=-5e-4)
+    t_opt = time.perf_counter() - t0
+    sample_s = t_fwd + t_proj_fwd + t_r_fwd + t_bwd + t_opt
+    return dict(sample_s=sample_s, full_step_s=sample_s / frac, frac=frac, voxels=sv, rays=sr,
+                stages=dict(backbone_fwd=t_fwd, densify_projection_fwd=t_proj_fwd, render_fwd=t_r_fwd, backward=t_bwd,
+                            optimizer=t_opt))
+
+
+def config_dict(wl: dict, world: int) -> dict:
+    """Identical keys from both arms."""
+    return {"workload": wl["name"], "scenes_per_gpu_per_step": 1, "parallelism": f"dp{world}",
+            "projection": "SimpleConv3D-v1m1 (the nuScenes config's projection; the ScanNet config's UNet3D-v1m2 is "
+                          "SURVEY 8f-1)",
+            "l2": "per-step working set (dense volumes, render activations) exceeds the 126 MB L2"}
 
 
 def run_reference(args, wl: dict) -> None:
@@ -211,24 +298,32 @@ def run_reference(args, wl: dict) -> None:
     if rank != 0:
         return
     threads = host_threads()
-    sv, sr = min(wl["voxels"], 10_000), min(wl["rays"], 128)
-    times = []
-    for i in range(args.warmup + args.steps):
-        t = cpu_oracle_step(wl, sv, sr, threads)
+    n = args.warmup + args.steps
+    # calibration on 5 % of the workload, then a sample fraction that keeps the whole run within ~4 minutes
+    cal = cpu_oracle_step(wl, 0.05, threads)
+    budget = 240.0 / max(n, 1)
+    frac = min(1.0, max(0.05, 0.05 * budget / max(cal["sample_s"], 1e-3)))
+    log(f"cpu arm: calibration {cal['sample_s']:.1f} s at 5 % -> sample fraction {frac:.3f} per step")
+    times, last = [], None
+    for i in range(n):
+        last = cpu_oracle_step(wl, frac, threads)
         if i >= args.warmup:
-            times.append(t["full_step_s"])
+            times.append(last["full_step_s"])
     per_step = statistics.mean(times)
     value = wl["rays"] / per_step  # one host: the CPU arm does not scale with N
-    sample = (f"SpUNet-v1m1 fwd+bwd on {sv} voxels + NeuS render fwd+bwd (2nd order) on {sr} rays x "
-              f"{wl['s0'] + wl['si']} samples, extrapolated linearly to {wl['voxels']} voxels / {wl['rays']} rays")
+    sample = (f"{frac:.3f} of the step per timed step ({last['voxels']} voxels, {last['rays']} rays x "
+              f"{wl['s0'] + wl['si']} samples, the same fraction of the dense grid): SpUNet fwd+bwd, densify, Conv3d "
+              f"projection, NeuS render fwd+bwd (2nd order), SGD update; measured {last['sample_s']:.1f} s, "
+              f"extrapolated linearly x{1 / frac:.1f}")
     print(json.dumps({
         "impl": "reference", "metric": "pretrain_rays_per_sec", "value": value, "unit": "rays/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["name"]},
-        "cpu_baseline": {"value": value, "unit": "rays/s", "cores": threads, "kind": "port", "sample": sample},
+        "scaling": "weak", "vs_baseline": None, "dtype": wl["dtype"], "data": "synthetic",
+        "config": config_dict(wl, args.gpus),
+        "cpu_baseline": {"value": value, "unit": "rays/s", "cores": threads, "kind": "port", "sample": sample,
+                         "stages_s": last["stages"], "run_to_run": [wl["rays"] / t for t in times]},
         "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "scenes_per_sec": 1.0 / per_step,
+        "scenes_per_sec": 1.0 / per_step, "voxels_per_sec": wl["voxels"] / per_step,
     }))
 
 
@@ -237,22 +332,57 @@ def build_model(wl: dict, dev):
     """Model (identical replicas: fixed seed), flat parameter/gradient buffers, SGD as in the reference configs
     (configs/scannet/pretrain-ponder-spunet-v1m1-0-base.py:96-98)."""
     from ponderv2_b200.dist import FlatParameters, broadcast_parameters
-    from ponderv2_b200.pretrain import PonderIndoorStep
+    from ponderv2_b200.pretrain import PonderIndoorStep, PonderOutdoorStep
     torch.manual_seed(1234)
-    model = PonderIndoorStep(backbone=dict(in_channels=6, num_classes=0), renderer=renderer_cfg(wl["s0"], wl["si"]),
-                             projection=dict(in_channels=96, out_channels=128), grid_shape=wl["grid_shape"],
-                             grid_size=0.02).to(dev).train()
-    flat = FlatParameters(model)
+    if wl["outdoor"]:
+        model = PonderOutdoorStep(backbone=dict(in_channels=4, num_classes=0),
+                                  renderer=outdoor_renderer_cfg(wl["s0"], wl["si"]),
+                                  projection=dict(in_channels=96, out_channels=32),
+                                  mask=dict(ratio=0.8, size=8, channel=4), scene_bbox=OUTDOOR_BBOX,
+                                  grid_shape=wl["grid_shape"], grid_size=(0.6, 0.6, 1.6)).to(dev).train()
+    else:
+        model = PonderIndoorStep(backbone=dict(in_channels=6, num_classes=0), renderer=renderer_cfg(wl["s0"], wl["si"]),
+                                 projection=dict(in_channels=96, out_channels=128), grid_shape=wl["grid_shape"],
+                                 grid_size=0.02).to(dev).train()
+    # flat buffers in backward-completion order: renderer, projection, then the backbone back to front
+    flat = FlatParameters(model, order=model.grad_completion_order(), num_chunks=4)
+    flat.freeze_untouched([n for n, _ in model.named_parameters() if "laplace_density" in n])
     broadcast_parameters(flat)
-    opt = torch.optim.SGD(flat.optimizer_params(), lr=5e-4, momentum=0.9, weight_decay=1e-4, nesterov=True)
+    flat.enable_overlap()
+    opt = flat.make_optimizer(torch.optim.SGD, lr=5e-4, momentum=0.9, weight_decay=1e-4, nesterov=True)
     return model, flat, opt
+
+
+def nccl_summary(path_glob: str) -> dict:
+    """Algorithm / protocol / transport lines NCCL logged for the all-reduce (NCCL_DEBUG=INFO to per-rank files)."""
+    import glob
+    import re
+    found = {"nvls": False, "channels": None, "algos": set(), "version": None}
+    for f in glob.glob(path_glob):
+        try:
+            txt = Path(f).read_text(errors="ignore")
+        except OSError:
+            continue
+        if re.search(r"NVLS", txt):
+            found["nvls"] = True
+        m = re.search(r"NCCL version ([0-9.+a-z]+)", txt)
+        if m:
+            found["version"] = m.group(1)
+        m = re.search(r"(\d+) coll channels", txt)
+        if m:
+            found["channels"] = int(m.group(1))
+        for a in re.findall(r"Algo(?:rithm)?[ =:]+(\w+)", txt):
+            found["algos"].add(a)
+        for a in ("Ring", "Tree", "NVLS", "CollNet"):
+            if re.search(rf"\b{a}\b", txt):
+                found["algos"].add(a)
+    found["algos"] = sorted(found["algos"])
+    return found
 
 
 def run_ours(args, wl: dict) -> None:
     import torch.distributed as dist
     from ponderv2_b200 import _lib
-    from ponderv2_b200.dist import FlatParameters, broadcast_parameters
-    from ponderv2_b200.pretrain import PonderIndoorStep
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -261,12 +391,20 @@ def run_ours(args, wl: dict) -> None:
         raise RuntimeError("bench.py --impl ours needs a CUDA device: ponderv2_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    nccl_log = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL's INFO log (algorithm, channels, NVLS) goes to per-rank files, never to the JSON line on stdout
+        nccl_log = tempfile.mkdtemp(prefix="pv2_nccl_")
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,COLL,TUNING")
+        os.environ.setdefault("NCCL_DEBUG_FILE", os.path.join(nccl_log, "rank%h.%p.log"))
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
 
     model, flat, opt = build_model(wl, dev)
+    autocast = (lambda: torch.autocast("cuda", dtype=torch.bfloat16)) if wl["dtype"] == "bf16" else \
+               (lambda: torch.autocast("cuda", enabled=False))
 
     # per-rank scene (seed = 1000*config + scene index), kept in pinned host memory
     scene = make_scene(wl, 1000 * wl["cfg_id"] + rank)
@@ -279,9 +417,10 @@ def run_ours(args, wl: dict) -> None:
     def step(inputs: dict) -> torch.Tensor:
         data = dict(inputs)
         data["sparse_shape"] = shape
-        flat.zero_grad()
-        out = model(data)
-        out["loss"].backward()
+        opt.zero_grad()                     # the flat gradient buffer is zeroed, views stay attached
+        with autocast():
+            out = model(data)
+        out["loss"].backward()              # gradient slices are all-reduced from hooks while this runs (N > 1)
         flat.all_reduce_mean()
         opt.step()
         return out["loss"].detach()
@@ -329,12 +468,14 @@ def run_ours(args, wl: dict) -> None:
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    ms_dev, launches, last_loss = timed_loop(from_host=False, profile=True)
-    prof = _lib.PROFILE.summary()
+    ms_dev, launches, last_loss = timed_loop(from_host=False, profile=False)      # `value`: un-instrumented
     log(f"device-resident loop: {ms_dev / args.steps:.2f} ms/step")
     ms_e2e, _, _ = timed_loop(from_host=True, profile=False)
     log(f"host-fed loop: {ms_e2e / args.steps:.2f} ms/step")
     clk = clocks.stop() if rank == 0 else None
+    ms_prof, _, _ = timed_loop(from_host=False, profile=True)                     # per-kernel events: roofline only
+    prof = _lib.PROFILE.summary()
+    log(f"instrumented loop: {ms_prof / args.steps:.2f} ms/step")
 
     rays_per_step = wl["rays"] * world
     value = rays_per_step * args.steps / (ms_dev * 1e-3)
@@ -343,13 +484,17 @@ def run_ours(args, wl: dict) -> None:
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = host_threads()
-        sv, sr = min(wl["voxels"], 10_000), min(wl["rays"], 128)
         log(f"cpu baseline on {threads} threads ({os.cpu_count()} cores) ...")
-        t = cpu_oracle_step(wl, sv, sr, threads)
+        cal = cpu_oracle_step(wl, 0.05, threads)
+        frac = min(1.0, max(0.05, 0.05 * 20.0 / max(cal["sample_s"], 1e-3)))        # ~20 s of CPU work
+        t = cpu_oracle_step(wl, frac, threads)
         log(f"cpu baseline done: {t}")
         cpu = {"value": wl["rays"] / t["full_step_s"], "unit": "rays/s", "cores": threads, "kind": "port",
-               "sample": f"oracle SpUNet fwd+bwd on {sv} voxels ({t['backbone_s']:.1f} s) + NeuS fwd+bwd on {sr} rays "
-                         f"({t['render_s']:.1f} s), extrapolated linearly to the full step"}
+               "sample": f"{frac:.3f} of the step ({t['voxels']} voxels, {t['rays']} rays, same fraction of the dense "
+                         f"grid): oracle SpUNet + densify + projection + NeuS fwd+bwd + SGD measured {t['sample_s']:.1f} s, "
+                         f"extrapolated linearly x{1 / frac:.1f}; the 5 % calibration sample extrapolates to "
+                         f"{wl['rays'] / cal['full_step_s']:.1f} rays/s",
+               "stages_s": t["stages"]}
     if rank == 0:
         peaks = measured_peaks()
         gg = prof.get("pv2_spconv_gather_gemm", dict(calls=0, ms=0.0, bytes=0))
@@ -358,11 +503,10 @@ def run_ours(args, wl: dict) -> None:
         line = {
             "metric": "pretrain_rays_per_sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["name"], "scenes_per_gpu_per_step": 1, "parallelism": f"dp{world}",
-                       "projection": "SimpleConv3D-v1m1 96->128 (cuDNN; UNet3D-v1m2 is SURVEY 8f-1, out of scope)",
-                       "l2": "per-step working set (201 MB + 268 MB dense volumes) exceeds the 126 MB L2"},
+            "scaling": "weak", "vs_baseline": None, "dtype": wl["dtype"], "data": "synthetic",
+            "config": config_dict(wl, world),
             "scenes_per_sec": world * args.steps / (ms_dev * 1e-3),
+            "voxels_per_sec": wl["voxels"] * world * args.steps / (ms_dev * 1e-3),
             "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
@@ -374,10 +518,14 @@ def run_ours(args, wl: dict) -> None:
                          "algorithmic_bytes_per_launch": gg["bytes"] / max(gg["calls"], 1),
                          "peak_source": peaks["source"],
                          "launches": gg["calls"], "kernel_ms_per_step": gg["ms"] / args.steps,
-                         "share_of_step": gg["ms"] / max(ms_dev, 1e-9)},
+                         "share_of_step": gg["ms"] / max(ms_prof, 1e-9),
+                         "timed_in": "separate instrumented loop (CUDA events around each C-ABI call)"},
             "kernel_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()},
+            "instrumented_ms_per_step": ms_prof / args.steps,
             "cpu_baseline": cpu, "clocks": clk, "loss": last_loss,
         }
+        if nccl_log is not None:
+            line["nccl"] = nccl_summary(os.path.join(nccl_log, "*.log"))
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -38,6 +38,12 @@ const char* pv2_error_string(int code);
 int64_t pv2_launch_count(void);
 /* Number of SMs the library sized its persistent grids for (148 on B200); 0 if no device. */
 int pv2_sm_count(void);
+/* Kernel-selection switches for A/B measurements and tests (defaults: environment PV2_GG_TMA / PV2_GG_BX3 / PV2_WGRAD_MN,
+ * read once).  "gg_tma": bf16 gather through TMA gather4 (-1 auto by size, 0 off, 1 on); "gg_bx3": fp32 gather-GEMM as
+ * bf16x3 (0 / 1); "wgrad_mn": MN-major bf16 weight-gradient kernel (0 / 1).  Results never depend on them beyond the
+ * stated tolerances.  set: 0 / PV2_EINVAL; get: the value, -1 for an unknown name. */
+int pv2_set_option(const char* name, int value);
+int pv2_get_option(const char* name);
 
 /* ------------------------------------------------------------------------------------------
  * Rulebook (neighbour-map) build.  Replaces spconv's indice-pair generation that the first
@@ -140,6 +146,15 @@ int pv2_bn_act_fwd(const float* x, const float* res, const float* gamma, const f
 int pv2_bn_act_bwd(const float* x, const float* dy, const float* y, const float* gamma, const float* mean,
                    const float* invstd, int relu, int64_t n, int c, float* dx, float* dres, float* dgamma, float* dbeta,
                    void* workspace, size_t workspace_bytes, void* stream);
+/* The same two calls with the [n, c] feature matrices (x, res, y / dy, dx, dres) stored in `dtype` (PV2_F32 or
+ * PV2_BF16); statistics, gamma / beta and their gradients are always float32.  Replaces nn.BatchNorm1d under the
+ * reference's autocast (engines/train.py:183-196): half-precision activations, fp32 statistics. */
+int pv2_bn_act_fwd_t(const void* x, const void* res, const float* gamma, const float* beta, float* running_mean,
+                     float* running_var, float momentum, float eps, int relu, int64_t n, int c, void* y, float* mean,
+                     float* invstd, int dtype, void* workspace, size_t workspace_bytes, void* stream);
+int pv2_bn_act_bwd_t(const void* x, const void* dy, const void* y, const float* gamma, const float* mean,
+                     const float* invstd, int relu, int64_t n, int c, void* dx, void* dres, float* dgamma, float* dbeta,
+                     int dtype, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Densify: voxel features -> dense channels-last volume, scatter-mean

@@ -24,6 +24,8 @@ SIGNATURES = {
     "pv2_error_string": (C.c_char_p, [_int]),
     "pv2_sm_count": (_int, []),
     "pv2_launch_count": (_i64, []),
+    "pv2_set_option": (_int, [C.c_char_p, _int]),
+    "pv2_get_option": (_int, [C.c_char_p]),
     "pv2_rulebook_workspace_bytes": (_sz, [_i64]),
     "pv2_rulebook_subm": (_int, [_vp, _i64, C.POINTER(C.c_int32), _int, _vp, _vp, _vp, _sz, _vp]),
     "pv2_rulebook_down": (_int, [_vp, _i64, C.POINTER(C.c_int32), _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
@@ -59,6 +61,9 @@ SIGNATURES = {
     "pv2_bn_workspace_bytes": (_sz, [_i64, _int]),
     "pv2_bn_act_fwd": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_float, C.c_float, _int, _i64, _int, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pv2_bn_act_bwd": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _i64, _int, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "pv2_bn_act_fwd_t": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_float, C.c_float, _int, _i64, _int, _vp, _vp, _vp, _int, _vp, _sz,
+                                 _vp]),
+    "pv2_bn_act_bwd_t": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _i64, _int, _vp, _vp, _vp, _vp, _int, _vp, _sz, _vp]),
     "pv2_densify_fwd": (_int, [_vp, _vp, _i64, _int, _i64, _vp, _vp, _vp]),
     "pv2_densify_bwd": (_int, [_vp, _vp, _vp, _i64, _int, _vp, _vp]),
     "pv2_trilinear_fwd": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _int, _int, _int, _int, _vp]),

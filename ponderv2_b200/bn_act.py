@@ -4,7 +4,8 @@
 `relu(bn(x) + residual)` would (reference: BasicBlock.forward, spconv_unet_v1m1_base.py:70-83, and the conv-bn-relu
 blocks :111-180): batch statistics in training mode with the running buffers updated in place (momentum, unbiased
 variance, num_batches_tracked), so state_dicts stay interchangeable with the reference's.  Two kernels forward, two
-backward instead of torch's five and eight passes.  Eval mode (running statistics) is a plain affine map and stays torch.
+backward instead of torch's five and eight passes, for fp32 and bf16 features (statistics and parameters always fp32, as
+nn.BatchNorm1d under autocast).  Eval mode (running statistics) is a plain affine map and stays torch, with a one-time note.
 """
 from __future__ import annotations
 
@@ -24,17 +25,17 @@ class _BNActFunction(torch.autograd.Function):
         x = x.contiguous()
         n, c = x.shape
         dev = x.device
-        res_c = res.contiguous() if res is not None else None
+        res_c = res.contiguous().to(x.dtype) if res is not None else None
         y = torch.empty_like(x)
         stats = torch.empty((2, c), dtype=torch.float32, device=dev)
         ws_bytes = lib.pv2_bn_workspace_bytes(n, c)
         ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
-            _lib.check(lib.pv2_bn_act_fwd(_lib.ptr(x), _lib.ptr(res_c), _lib.ptr(gamma.contiguous()),
-                                          _lib.ptr(beta.contiguous()), _lib.ptr(running_mean), _lib.ptr(running_var),
-                                          float(momentum), float(eps), int(relu), n, c, _lib.ptr(y), _lib.ptr(stats[0]),
-                                          _lib.ptr(stats[1]), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
-                       "pv2_bn_act_fwd")
+            _lib.check(lib.pv2_bn_act_fwd_t(_lib.ptr(x), _lib.ptr(res_c), _lib.ptr(gamma.contiguous()),
+                                            _lib.ptr(beta.contiguous()), _lib.ptr(running_mean), _lib.ptr(running_var),
+                                            float(momentum), float(eps), int(relu), n, c, _lib.ptr(y), _lib.ptr(stats[0]),
+                                            _lib.ptr(stats[1]), _lib.dtype_code(x.dtype), _lib.ptr(ws), ws.numel(),
+                                            _lib.stream_ptr()), "pv2_bn_act_fwd_t")
         ctx.save_for_backward(x, y, gamma, stats)
         ctx.relu, ctx.has_res = bool(relu), res is not None
         return y
@@ -45,23 +46,36 @@ class _BNActFunction(torch.autograd.Function):
         lib = _lib.load()
         n, c = x.shape
         dev = x.device
-        dy = dy.contiguous()
+        dy = dy.contiguous().to(x.dtype)
         dx = torch.empty_like(x)
         dres = torch.empty_like(x) if ctx.has_res else None
         dgb = torch.empty((2, c), dtype=torch.float32, device=dev)
         ws_bytes = lib.pv2_bn_workspace_bytes(n, c)
         ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
-            _lib.check(lib.pv2_bn_act_bwd(_lib.ptr(x), _lib.ptr(dy), _lib.ptr(y), _lib.ptr(gamma.contiguous()),
-                                          _lib.ptr(stats[0]), _lib.ptr(stats[1]), int(ctx.relu), n, c, _lib.ptr(dx),
-                                          _lib.ptr(dres), _lib.ptr(dgb[0]), _lib.ptr(dgb[1]), _lib.ptr(ws), ws.numel(),
-                                          _lib.stream_ptr()), "pv2_bn_act_bwd")
+            _lib.check(lib.pv2_bn_act_bwd_t(_lib.ptr(x), _lib.ptr(dy), _lib.ptr(y), _lib.ptr(gamma.contiguous()),
+                                            _lib.ptr(stats[0]), _lib.ptr(stats[1]), int(ctx.relu), n, c, _lib.ptr(dx),
+                                            _lib.ptr(dres), _lib.ptr(dgb[0]), _lib.ptr(dgb[1]), _lib.dtype_code(x.dtype),
+                                            _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), "pv2_bn_act_bwd_t")
         return dx, dres, dgb[0], dgb[1], None, None, None, None, None
 
 
+_NOTED = set()
+
+
+def _note_fallback(x: torch.Tensor, bn: nn.BatchNorm1d) -> None:
+    """One warning per reason when a call leaves the fused kernels (eval-mode statistics are a plain affine map and stay
+    torch by design; anything else is a shape / dtype the kernels do not take)."""
+    why = "eval mode (running statistics)" if not bn.training else f"dtype {x.dtype}, shape {tuple(x.shape)}"
+    if why not in _NOTED:
+        _NOTED.add(why)
+        import warnings
+        warnings.warn(f"bn_act: torch BatchNorm1d path taken: {why}", RuntimeWarning, stacklevel=3)
+
+
 def supported(x: torch.Tensor, bn: nn.BatchNorm1d) -> bool:
-    return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.shape[0] > 1 and x.shape[1] % 4 == 0
-            and x.shape[1] <= 1024 and bn.affine and bn.weight.dtype == torch.float32)
+    return (x.is_cuda and x.dtype in (torch.float32, torch.bfloat16) and x.dim() == 2 and x.shape[0] > 1
+            and x.shape[1] % 4 == 0 and x.shape[1] <= 1024 and bn.affine and bn.weight.dtype == torch.float32)
 
 
 def bn_act(x: torch.Tensor, bn: nn.BatchNorm1d, residual: Optional[torch.Tensor] = None, relu: bool = True) -> torch.Tensor:
@@ -75,6 +89,8 @@ def bn_act(x: torch.Tensor, bn: nn.BatchNorm1d, residual: Optional[torch.Tensor]
         rm = bn.running_mean if bn.track_running_stats else None
         rv = bn.running_var if bn.track_running_stats else None
         return _BNActFunction.apply(x, residual, bn.weight, bn.bias, rm, rv, float(momentum or 0.0), float(bn.eps), relu)
+    if x.is_cuda:
+        _note_fallback(x, bn)
     out = bn(x)
     if residual is not None:
         out = out + residual

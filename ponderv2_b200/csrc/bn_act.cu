@@ -11,14 +11,39 @@
 
 namespace {
 
+// four consecutive channels of an [N, C] feature matrix stored as fp32 (16 B) or bf16 (8 B); arithmetic is fp32 either way
+template <bool kBf16>
+__device__ __forceinline__ float4 ld4(const void* base, int64_t i) {
+  if constexpr (kBf16) {
+    const uint2 u = __ldg(reinterpret_cast<const uint2*>(base) + i);
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+  } else {
+    return __ldg(reinterpret_cast<const float4*>(base) + i);
+  }
+}
+template <bool kBf16>
+__device__ __forceinline__ void st4(void* base, int64_t i, const float4& v) {
+  if constexpr (kBf16) {
+    const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<const uint32_t*>(&a);
+    u.y = *reinterpret_cast<const uint32_t*>(&b);
+    reinterpret_cast<uint2*>(base)[i] = u;
+  } else {
+    reinterpret_cast<float4*>(base)[i] = v;
+  }
+}
+
 constexpr int kRowsPerBlock = 64;    // many small blocks: the reduction passes are latency-bound at 100 k rows
 constexpr int kBnThreads = 256;
 
 // Per-block column sums of up to two quantities.  Thread t owns channel group (t % C4) and rows (t / C4) + i * RP.
 // MODE 0: (x, x*x).  MODE 1: (dz, dz * xhat) with dz = dy * (y > 0 if relu), xhat = (x - mean) * invstd.
-template <int MODE>
-__global__ void __launch_bounds__(kBnThreads) bn_partial_kernel(const float4* __restrict__ x, const float4* __restrict__ dy,
-                                                                const float4* __restrict__ y, const float* __restrict__ mean,
+template <int MODE, bool kBf16>
+__global__ void __launch_bounds__(kBnThreads) bn_partial_kernel(const void* __restrict__ x, const void* __restrict__ dy,
+                                                                const void* __restrict__ y, const float* __restrict__ mean,
                                                                 const float* __restrict__ invstd, int64_t N, int C4, int relu,
                                                                 float4* __restrict__ partial /*[nblk][2][C4]*/) {
   __shared__ float4 sa[kBnThreads], sb[kBnThreads];
@@ -39,14 +64,14 @@ __global__ void __launch_bounds__(kBnThreads) bn_partial_kernel(const float4* __
 #pragma unroll 4
     for (int64_t r = rt; r < rows; r += RP) {
       const int64_t e = (row0 + r) * C4 + cg;
-      const float4 v = __ldg(&x[e]);
+      const float4 v = ld4<kBf16>(x, e);
       if (MODE == 0) {
         a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
         b.x = fmaf(v.x, v.x, b.x); b.y = fmaf(v.y, v.y, b.y); b.z = fmaf(v.z, v.z, b.z); b.w = fmaf(v.w, v.w, b.w);
       } else {
-        float4 g = __ldg(&dy[e]);
+        float4 g = ld4<kBf16>(dy, e);
         if (relu) {
-          const float4 o = __ldg(&y[e]);
+          const float4 o = ld4<kBf16>(y, e);
           g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f; g.z = o.z > 0.f ? g.z : 0.f; g.w = o.w > 0.f ? g.w : 0.f;
         }
         a.x += g.x; a.y += g.y; a.z += g.z; a.w += g.w;
@@ -113,31 +138,33 @@ __global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restri
 }
 
 // y = [relu]((x - mean) * invstd * gamma + beta [+ res])
-__global__ void bn_apply_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ res, const float* __restrict__ mean,
+template <bool kBf16>
+__global__ void bn_apply_fwd_kernel(const void* __restrict__ x, const void* __restrict__ res, const float* __restrict__ mean,
                                     const float* __restrict__ invstd, const float* __restrict__ gamma,
-                                    const float* __restrict__ beta, int64_t total4, int C4, int relu, float4* __restrict__ y) {
+                                    const float* __restrict__ beta, int64_t total4, int C4, int relu, void* __restrict__ y) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
     const int cg = (int)(i % C4);
     const float4 mu = *reinterpret_cast<const float4*>(mean + cg * 4);
     const float4 is = *reinterpret_cast<const float4*>(invstd + cg * 4);
     const float4 ga = *reinterpret_cast<const float4*>(gamma + cg * 4);
     const float4 be = *reinterpret_cast<const float4*>(beta + cg * 4);
-    const float4 v = __ldg(&x[i]);
+    const float4 v = ld4<kBf16>(x, i);
     float4 o;
     o.x = (v.x - mu.x) * is.x * ga.x + be.x; o.y = (v.y - mu.y) * is.y * ga.y + be.y;
     o.z = (v.z - mu.z) * is.z * ga.z + be.z; o.w = (v.w - mu.w) * is.w * ga.w + be.w;
-    if (res != nullptr) { const float4 r = __ldg(&res[i]); o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w; }
+    if (res != nullptr) { const float4 r = ld4<kBf16>(res, i); o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w; }
     if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-    y[i] = o;
+    st4<kBf16>(y, i, o);
   }
 }
 
 // dz = dy * (y > 0 if relu);  dx = gamma * invstd * (dz - dbeta / N - xhat * dgamma / N);  dres = dz
-__global__ void bn_apply_bwd_kernel(const float4* __restrict__ x, const float4* __restrict__ dy, const float4* __restrict__ y,
+template <bool kBf16>
+__global__ void bn_apply_bwd_kernel(const void* __restrict__ x, const void* __restrict__ dy, const void* __restrict__ y,
                                     const float* __restrict__ mean, const float* __restrict__ invstd,
                                     const float* __restrict__ gamma, const float* __restrict__ dgamma,
                                     const float* __restrict__ dbeta, int64_t total4, int C4, int relu, float inv_n,
-                                    float4* __restrict__ dx, float4* __restrict__ dres) {
+                                    void* __restrict__ dx, void* __restrict__ dres) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
     const int cg = (int)(i % C4);
     const float4 mu = *reinterpret_cast<const float4*>(mean + cg * 4);
@@ -145,19 +172,19 @@ __global__ void bn_apply_bwd_kernel(const float4* __restrict__ x, const float4* 
     const float4 ga = *reinterpret_cast<const float4*>(gamma + cg * 4);
     const float4 dg = *reinterpret_cast<const float4*>(dgamma + cg * 4);
     const float4 db = *reinterpret_cast<const float4*>(dbeta + cg * 4);
-    const float4 v = __ldg(&x[i]);
-    float4 g = __ldg(&dy[i]);
+    const float4 v = ld4<kBf16>(x, i);
+    float4 g = ld4<kBf16>(dy, i);
     if (relu) {
-      const float4 o = __ldg(&y[i]);
+      const float4 o = ld4<kBf16>(y, i);
       g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f; g.z = o.z > 0.f ? g.z : 0.f; g.w = o.w > 0.f ? g.w : 0.f;
     }
-    if (dres != nullptr) dres[i] = g;
+    if (dres != nullptr) st4<kBf16>(dres, i, g);
     float4 d;
     d.x = ga.x * is.x * (g.x - db.x * inv_n - (v.x - mu.x) * is.x * dg.x * inv_n);
     d.y = ga.y * is.y * (g.y - db.y * inv_n - (v.y - mu.y) * is.y * dg.y * inv_n);
     d.z = ga.z * is.z * (g.z - db.z * inv_n - (v.z - mu.z) * is.z * dg.z * inv_n);
     d.w = ga.w * is.w * (g.w - db.w * inv_n - (v.w - mu.w) * is.w * dg.w * inv_n);
-    dx[i] = d;
+    st4<kBf16>(dx, i, d);
   }
 }
 
@@ -173,47 +200,92 @@ size_t pv2_bn_workspace_bytes(int64_t n, int c) {
   return ((size_t)nblocks_for(n) * 2 * c * sizeof(float) + 255) / 256 * 256;
 }
 
-int pv2_bn_act_fwd(const float* x, const float* res, const float* gamma, const float* beta, float* running_mean,
-                   float* running_var, float momentum, float eps, int relu, int64_t n, int c, float* y, float* mean,
-                   float* invstd, void* workspace, size_t workspace_bytes, void* stream_) {
+}  // extern "C"
+
+template <bool kBf16>
+static int bn_fwd_t(const void* x, const void* res, const float* gamma, const float* beta, float* running_mean,
+                    float* running_var, float momentum, float eps, int relu, int64_t n, int c, void* y, float* mean,
+                    float* invstd, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   PV2_CHECK_ARG(shape_ok(n, c));
   if (n == 0) return 0;
   PV2_CHECK_ARG(x && gamma && beta && y && mean && invstd && workspace);
-  PV2_CHECK_ARG((((uintptr_t)x | (uintptr_t)y | (uintptr_t)res | (uintptr_t)mean | (uintptr_t)invstd | (uintptr_t)gamma |
-                  (uintptr_t)beta) & 15) == 0);
+  const uintptr_t io_mask = kBf16 ? 7 : 15;
+  PV2_CHECK_ARG((((uintptr_t)x | (uintptr_t)y | (uintptr_t)res) & io_mask) == 0);
+  PV2_CHECK_ARG((((uintptr_t)mean | (uintptr_t)invstd | (uintptr_t)gamma | (uintptr_t)beta) & 15) == 0);
   if (workspace_bytes < pv2_bn_workspace_bytes(n, c)) return PV2_EWORKSPACE;
-  cudaStream_t stream = (cudaStream_t)stream_;
   const int nblk = nblocks_for(n), C4 = c / 4;
-  bn_partial_kernel<0><<<nblk, kBnThreads, 0, stream>>>((const float4*)x, nullptr, nullptr, nullptr, nullptr, n, C4, 0,
-                                                         (float4*)workspace);
+  bn_partial_kernel<0, kBf16><<<nblk, kBnThreads, 0, stream>>>(x, nullptr, nullptr, nullptr, nullptr, n, C4, 0,
+                                                                (float4*)workspace);
   bn_finalize_kernel<0><<<(c + 31) / 32, 1024, 0, stream>>>((const float*)workspace, nblk, c, n, eps, momentum, mean, invstd,
                                                              running_mean, running_var);
   const int64_t total4 = n * C4;
-  bn_apply_fwd_kernel<<<pv2_grid_for(total4, 256), 256, 0, stream>>>((const float4*)x, (const float4*)res, mean, invstd, gamma, beta,
-                                                                    total4, C4, relu, (float4*)y);
+  bn_apply_fwd_kernel<kBf16><<<pv2_grid_for(total4, 256), 256, 0, stream>>>(x, res, mean, invstd, gamma, beta, total4, C4,
+                                                                           relu, y);
   PV2_DONE(3);
+}
+
+template <bool kBf16>
+static int bn_bwd_t(const void* x, const void* dy, const void* y, const float* gamma, const float* mean,
+                    const float* invstd, int relu, int64_t n, int c, void* dx, void* dres, float* dgamma, float* dbeta,
+                    void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  PV2_CHECK_ARG(shape_ok(n, c));
+  if (n == 0) return 0;
+  PV2_CHECK_ARG(x && dy && gamma && mean && invstd && dx && dgamma && dbeta && workspace && (!relu || y));
+  const uintptr_t io_mask = kBf16 ? 7 : 15;
+  PV2_CHECK_ARG((((uintptr_t)x | (uintptr_t)dy | (uintptr_t)y | (uintptr_t)dx | (uintptr_t)dres) & io_mask) == 0);
+  PV2_CHECK_ARG((((uintptr_t)mean | (uintptr_t)invstd | (uintptr_t)gamma | (uintptr_t)dgamma | (uintptr_t)dbeta) & 15) == 0);
+  if (workspace_bytes < pv2_bn_workspace_bytes(n, c)) return PV2_EWORKSPACE;
+  const int nblk = nblocks_for(n), C4 = c / 4;
+  bn_partial_kernel<1, kBf16><<<nblk, kBnThreads, 0, stream>>>(x, dy, y, mean, invstd, n, C4, relu, (float4*)workspace);
+  bn_finalize_kernel<1><<<(c + 31) / 32, 1024, 0, stream>>>((const float*)workspace, nblk, c, n, 0.f, 0.f, dgamma, dbeta, nullptr,
+                                                             nullptr);
+  const int64_t total4 = n * C4;
+  bn_apply_bwd_kernel<kBf16><<<pv2_grid_for(total4, 256), 256, 0, stream>>>(x, dy, y, mean, invstd, gamma, dgamma, dbeta,
+                                                                           total4, C4, relu, 1.0f / (float)n, dx, dres);
+  PV2_DONE(3);
+}
+
+extern "C" {
+
+int pv2_bn_act_fwd(const float* x, const float* res, const float* gamma, const float* beta, float* running_mean,
+                   float* running_var, float momentum, float eps, int relu, int64_t n, int c, float* y, float* mean,
+                   float* invstd, void* workspace, size_t workspace_bytes, void* stream_) {
+  return bn_fwd_t<false>(x, res, gamma, beta, running_mean, running_var, momentum, eps, relu, n, c, y, mean, invstd,
+                         workspace, workspace_bytes, (cudaStream_t)stream_);
 }
 
 int pv2_bn_act_bwd(const float* x, const float* dy, const float* y, const float* gamma, const float* mean,
                    const float* invstd, int relu, int64_t n, int c, float* dx, float* dres, float* dgamma, float* dbeta,
                    void* workspace, size_t workspace_bytes, void* stream_) {
-  PV2_CHECK_ARG(shape_ok(n, c));
-  if (n == 0) return 0;
-  PV2_CHECK_ARG(x && dy && gamma && mean && invstd && dx && dgamma && dbeta && workspace && (!relu || y));
-  PV2_CHECK_ARG((((uintptr_t)x | (uintptr_t)dy | (uintptr_t)y | (uintptr_t)dx | (uintptr_t)dres | (uintptr_t)mean |
-                  (uintptr_t)invstd | (uintptr_t)gamma | (uintptr_t)dgamma | (uintptr_t)dbeta) & 15) == 0);
-  if (workspace_bytes < pv2_bn_workspace_bytes(n, c)) return PV2_EWORKSPACE;
-  cudaStream_t stream = (cudaStream_t)stream_;
-  const int nblk = nblocks_for(n), C4 = c / 4;
-  bn_partial_kernel<1><<<nblk, kBnThreads, 0, stream>>>((const float4*)x, (const float4*)dy, (const float4*)y, mean, invstd, n, C4,
-                                                         relu, (float4*)workspace);
-  bn_finalize_kernel<1><<<(c + 31) / 32, 1024, 0, stream>>>((const float*)workspace, nblk, c, n, 0.f, 0.f, dgamma, dbeta, nullptr,
-                                                             nullptr);
-  const int64_t total4 = n * C4;
-  bn_apply_bwd_kernel<<<pv2_grid_for(total4, 256), 256, 0, stream>>>((const float4*)x, (const float4*)dy, (const float4*)y, mean,
-                                                                    invstd, gamma, dgamma, dbeta, total4, C4, relu,
-                                                                    1.0f / (float)n, (float4*)dx, (float4*)dres);
-  PV2_DONE(3);
+  return bn_bwd_t<false>(x, dy, y, gamma, mean, invstd, relu, n, c, dx, dres, dgamma, dbeta, workspace, workspace_bytes,
+                         (cudaStream_t)stream_);
+}
+
+/* Same with the [n, c] feature matrices (x, res, y / dy, dx, dres) in `dtype` (PV2_F32 or PV2_BF16): the bf16 backbone
+ * of BASELINE configs[2] (the reference runs fp16 autocast: BatchNorm takes half inputs, keeps fp32 statistics and
+ * parameters, returns half).  Statistics, gamma / beta and their gradients stay fp32. */
+int pv2_bn_act_fwd_t(const void* x, const void* res, const float* gamma, const float* beta, float* running_mean,
+                     float* running_var, float momentum, float eps, int relu, int64_t n, int c, void* y, float* mean,
+                     float* invstd, int dtype, void* workspace, size_t workspace_bytes, void* stream_) {
+  if (dtype == PV2_F32)
+    return bn_fwd_t<false>(x, res, gamma, beta, running_mean, running_var, momentum, eps, relu, n, c, y, mean, invstd,
+                           workspace, workspace_bytes, (cudaStream_t)stream_);
+  if (dtype == PV2_BF16)
+    return bn_fwd_t<true>(x, res, gamma, beta, running_mean, running_var, momentum, eps, relu, n, c, y, mean, invstd,
+                          workspace, workspace_bytes, (cudaStream_t)stream_);
+  return PV2_EUNSUPPORTED;
+}
+
+int pv2_bn_act_bwd_t(const void* x, const void* dy, const void* y, const float* gamma, const float* mean,
+                     const float* invstd, int relu, int64_t n, int c, void* dx, void* dres, float* dgamma, float* dbeta,
+                     int dtype, void* workspace, size_t workspace_bytes, void* stream_) {
+  if (dtype == PV2_F32)
+    return bn_bwd_t<false>(x, dy, y, gamma, mean, invstd, relu, n, c, dx, dres, dgamma, dbeta, workspace, workspace_bytes,
+                           (cudaStream_t)stream_);
+  if (dtype == PV2_BF16)
+    return bn_bwd_t<true>(x, dy, y, gamma, mean, invstd, relu, n, c, dx, dres, dgamma, dbeta, workspace, workspace_bytes,
+                          (cudaStream_t)stream_);
+  return PV2_EUNSUPPORTED;
 }
 
 }  // extern "C"

@@ -1,6 +1,7 @@
 // Library-level entry points and the dispatcher between the tensor-core and SIMT sparse-conv kernels.
 #include "pv2_common.cuh"
 #include <stdlib.h>
+#include <string.h>
 
 extern "C" {
 
@@ -15,6 +16,26 @@ int64_t pv2_launch_count(void) { return (int64_t)__atomic_load_n(&g_launches, __
 
 int pv2_spconv_gather_gemm_umma(const void*, const void*, int64_t, int64_t, const float*, const int32_t*, const int32_t*,
                                 void*, int64_t, int64_t, int, int, int, int, void*, size_t, void*);
+
+// ---- runtime options (development / A-B switches).  Defaults come from the environment once; tests and benchmarks set
+// them through pv2_set_option.  Names: "gg_tma" (bf16 gather through TMA gather4: -1 auto by size, 0 off, 1 on),
+// "gg_bx3" (fp32 gather-GEMM as bf16x3: 0 / 1), "wgrad_mn" (MN-major bf16 weight-gradient kernel: 0 / 1).
+static int g_opt_gg_tma = -2, g_opt_gg_bx3 = -2, g_opt_wgrad_mn = -2;
+static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
+int pv2_get_option(const char* name) {
+  if (name == nullptr) return -1;
+  if (!strcmp(name, "gg_tma")) { if (g_opt_gg_tma == -2) g_opt_gg_tma = env_int("PV2_GG_TMA", -1); return g_opt_gg_tma; }
+  if (!strcmp(name, "gg_bx3")) { if (g_opt_gg_bx3 == -2) g_opt_gg_bx3 = env_int("PV2_GG_BX3", 1); return g_opt_gg_bx3; }
+  if (!strcmp(name, "wgrad_mn")) { if (g_opt_wgrad_mn == -2) g_opt_wgrad_mn = env_int("PV2_WGRAD_MN", 1); return g_opt_wgrad_mn; }
+  return -1;
+}
+int pv2_set_option(const char* name, int value) {
+  if (name == nullptr) return PV2_EINVAL;
+  if (!strcmp(name, "gg_tma")) { g_opt_gg_tma = value; return 0; }
+  if (!strcmp(name, "gg_bx3")) { g_opt_gg_bx3 = value; return 0; }
+  if (!strcmp(name, "wgrad_mn")) { g_opt_wgrad_mn = value; return 0; }
+  return PV2_EINVAL;
+}
 
 static int force_simt() {
   static int v = -1;
@@ -63,9 +84,7 @@ int pv2_spconv_wgrad(const void* x, const void* dy, const int32_t* nbr, const in
                      const uint8_t* blk_active, float* dw, int64_t n_in, int64_t n_out, int cin, int cout, int kvol,
                      int dtype, void* workspace, size_t workspace_bytes, void* stream) {
   // second-generation kernel: MN-major bf16 operands (fp32 storage as bf16x3), no transposes, no scratch
-  static int use_mn = -1;
-  if (use_mn < 0) { const char* e = getenv("PV2_WGRAD_MN"); use_mn = (e && e[0] == '0') ? 0 : 1; }   // development A/B switch
-  if (!force_simt() && use_mn) {
+  if (!force_simt() && pv2_get_option("wgrad_mn") != 0) {
     int rc = pv2_wgrad_mn(x, dy, nbr, row_order, blk_active, dw, n_in, n_out, cin, cout, kvol, dtype, stream);
     if (rc != PV2_EUNSUPPORTED) return rc;
   }

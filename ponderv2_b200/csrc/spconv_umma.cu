@@ -28,6 +28,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+extern "C" int pv2_get_option(const char* name);   // capi.cu
+
 namespace {
 
 using namespace pv2;
@@ -1260,9 +1262,12 @@ int launch_persistent(const GGParams& p0, cudaStream_t stream, const void* w2 = 
 
 // bf16 storage through TMA gather4.  PV2_EUNSUPPORTED -> the caller uses the cp.async kernel.
 int launch_tma_bf16(const GGParams& p0, cudaStream_t stream, int64_t n_in, const void* w_full, int cout_full) {
-  static int enabled = -1;
-  if (enabled < 0) { const char* e = getenv("PV2_GG_TMA"); enabled = (e && e[0] == '0') ? 0 : 1; }   // development A/B switch
-  if (!enabled || tensor_map_encoder() == nullptr) return PV2_EUNSUPPORTED;
+  // Measured on B200 (profiles/r2e_micro_bf16_*.txt): the copy engine takes ~40-70 cycles per gather4 (four 128-byte
+  // rows), i.e. 13-18 B/clk/SM -- faster than the cp.async producers only for long, narrow launches (1 M voxels x 64
+  // channels: 349 vs 451 us), slower for 128 channels or ~100 k voxels.  "auto" follows that crossover.
+  const int mode = pv2_get_option("gg_tma");
+  if (mode == 0 || tensor_map_encoder() == nullptr) return PV2_EUNSUPPORTED;
+  if (mode < 0 && !(p0.cin == 64 && p0.n_out >= 262144)) return PV2_EUNSUPPORTED;
   GGParams p = p0;
   if ((p.cin & 63) != 0 || p.nbr == nullptr || p.x_row != p.cin || p.w_sk != p.cin || p.w_sco != (int64_t)p.kvol * p.cin)
     return PV2_EUNSUPPORTED;
@@ -1380,11 +1385,7 @@ static int fp32_groups(int cout, int kvol, int cin) {
 
 extern "C" {
 
-static int bx3_enabled() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("PV2_GG_BX3"); v = (e && e[0] == '0') ? 0 : 1; }   // development A/B switch
-  return v;
-}
+static int bx3_enabled() { return pv2_get_option("gg_bx3") != 0; }
 
 // fp32: room for the weights pre-split into bf16 hi / lo matrices (the bf16x3 kernel's TMA operand); bf16: none.
 size_t pv2_spconv_workspace_bytes(int64_t n_in, int cin, int cout, int kvol, int dtype) {

@@ -146,7 +146,9 @@ class FlatParameters:
         idx = []
         for x in names_or_params:
             p = named[x] if isinstance(x, str) else x
-            idx.append(next(i for i, q in enumerate(self.params) if q is p))
+            i = next((i for i, q in enumerate(self.params) if q is p), None)
+            if i is not None:              # parameters without requires_grad are not in the buffers anyway
+                idx.append(i)
         self._frozen = (idx, [self.params[i].detach().clone() for i in idx])
 
     # ------------------------------------------------------------------------------------------ collective
@@ -177,7 +179,7 @@ class FlatParameters:
     def enable_overlap(self, group=None) -> None:
         """Issue each slice's all-reduce on a side stream from a gradient hook, as soon as every parameter of the slice
         has its gradient (completion order = buffer order, so early slices go out while backward is still running)."""
-        if self._overlap:
+        if self._overlap or not _is_dist(group):   # single process: nothing to overlap, no per-parameter hooks
             return
         self._overlap, self._group = True, group
         if self.flat_grad.is_cuda:

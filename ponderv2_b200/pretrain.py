@@ -63,6 +63,29 @@ class _SceneViews(torch.autograd.Function):
         return out
 
 
+def _completion_order(step: nn.Module) -> list:
+    """Parameters in the order backward finishes their gradients (first = earliest): renderer, projection, then the
+    backbone from its last executed block to its first (SpUNetBase.forward: conv_input, (down, enc) x 4, (up, dec) x 4
+    from the deepest stage up).  FlatParameters lays the gradient buffer out in this order so that contiguous slices
+    complete early and can be all-reduced while backward is still running."""
+    bb = step.backbone
+    mods = [step.renderer, step.proj_net, bb.final]
+    for s in range(bb.num_stages):
+        mods += [bb.dec[s], bb.up[s]]
+    for s in reversed(range(bb.num_stages)):
+        mods += [bb.enc[s], bb.down[s]]
+    mods.append(bb.conv_input)
+    out, seen = [], set()
+    for m in mods:
+        for p in reversed(list(m.parameters())):
+            if id(p) not in seen:
+                seen.add(id(p)); out.append(p)
+    for p in step.parameters():            # anything not covered above (mtoken, ...)
+        if id(p) not in seen:
+            seen.add(id(p)); out.append(p)
+    return out
+
+
 class PonderIndoorStep(nn.Module):
     def __init__(self, backbone: dict, renderer: dict, projection: Optional[dict] = None,
                  grid_shape: Sequence[int] = (128, 128, 32), grid_size: float = 0.02, pool_type: str = "mean",
@@ -78,6 +101,9 @@ class PonderIndoorStep(nn.Module):
         self.renderer = build_renderer(renderer)
         self.grid_shape = tuple(int(g) for g in grid_shape)
         self.grid_size = float(grid_size)
+
+    def grad_completion_order(self) -> list:
+        return _completion_order(self)
 
     def to_dense(self, data_dict) -> torch.Tensor:
         offset = data_dict["offset"]
@@ -137,6 +163,9 @@ class PonderOutdoorStep(nn.Module):
             tok = nn.Parameter(torch.zeros(1, int(self.mask["channel"])))
             nn.init.trunc_normal_(tok, mean=0.0, std=0.02, a=-0.02, b=0.02)
             self.register_parameter("mtoken", tok)
+
+    def grad_completion_order(self) -> list:
+        return _completion_order(self)
 
     # -- extract_feature (:93-139): random block masking of the input features, then the backbone
     def mask_features(self, grid_coord, feat, offset, noise: Optional[torch.Tensor] = None):

@@ -266,8 +266,9 @@ def test_spunet_backbone_matches_oracle(cuda_lib):
     from tests.conftest import record
     record("spunet_backbone_matches_oracle", fwd=err, grad_joint=joint, grad_worst=worst, worst_name=worst_name)
     print("backbone grad err: joint", joint, "worst", worst_name, worst)
-    assert joint < 2e-2, joint
-    assert worst < 0.2, (worst_name, worst)
+    # measured on B200 (profiles/r2d_parity_report.jsonl): joint 6.6e-3, worst tensor 1.2e-2 (enc.0.block1.bn2.weight)
+    assert joint < 1.5e-2, joint
+    assert worst < 4e-2, (worst_name, worst)
 
 
 def test_spunet_state_dict_contract(cuda_lib):
@@ -510,6 +511,129 @@ def test_full_size_conv_matches_oracle(cuda_lib, cin, cout):
     # fp32 storage, fp32-grade tensor-core products, fp32 accumulation over 27 * cin terms (y, dx) / ~1e5 rows (dw, db)
     for k, v in errs.items():
         assert v < 1e-4, (k, v, errs)
+
+
+@pytest.mark.parametrize("cin,cout,tma", [(64, 64, 1), (128, 64, 1), (64, 128, 0), (256, 256, 1), (96, 96, 0)])
+def test_full_size_conv_bf16_matches_oracle(cuda_lib, cin, cout, tma):
+    """bf16 storage at the BASELINE size (100 k voxels): forward, data gradient and weight gradient against the fp64
+    oracle fed with the same bf16-rounded inputs.  tma = 1 forces the TMA gather4 kernel (UTMALDG.2D.GATHER4: missing
+    neighbours are out-of-bounds row indices the copy engine zero-fills), tma = 0 the cp.async kernel; the weight gradient
+    is the MN-major tcgen05 kernel in both.  bf16 outputs: <= 2^-8 relative per element on top of fp32 accumulation."""
+    import ponderv2_b200.spconv.pytorch as spconv
+    from tests.conftest import record
+    dev = _dev()
+    n = 100_000
+    ind, shape = _indoor_indices(n, 2000)
+    torch.manual_seed(cin + 3 * cout)
+    cuda_lib.pv2_set_option(b"gg_tma", tma)
+    try:
+        mod = spconv.SubMConv3d(cin, cout, 3, padding=1, bias=False, indice_key="k").to(dev)
+        with torch.no_grad():
+            mod.weight.normal_(0.0, 0.05)
+        xb = torch.randn(n, cin, device=dev).to(torch.bfloat16)
+        gb = torch.randn(n, cout, device=dev).to(torch.bfloat16)
+        xg = xb.clone().requires_grad_(True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out = mod(spconv.SparseConvTensor(xg, torch.from_numpy(ind).to(dev), shape, 1)).features
+        assert out.dtype == torch.bfloat16
+        out.backward(gb)
+    finally:
+        cuda_lib.pv2_set_option(b"gg_tma", -1)
+    w64 = mod.weight.detach().to(torch.bfloat16).cpu().double().requires_grad_(True)
+    xo = xb.cpu().double().requires_grad_(True)
+    yo = so.subm_conv(so.OracleSparseTensor(xo, ind, shape, 1), w64, None, 3, "k").features
+    yo.backward(gb.cpu().double())
+    scale = lambda t: max(t.abs().max().item(), 1e-6)
+    errs = {
+        "y": (out.detach().cpu().double() - yo.detach()).abs().max().item() / scale(yo),
+        "dx": (xg.grad.cpu().double() - xo.grad).abs().max().item() / scale(xo.grad),
+        "dw": (mod.weight.grad.cpu().double() - w64.grad).abs().max().item() / scale(w64.grad),
+    }
+    record("full_size_conv_bf16_matches_oracle", cin=cin, cout=cout, tma=tma, **errs)
+    assert errs["y"] < 1e-2 and errs["dx"] < 1e-2, errs      # bf16 output rounding (2^-8) relative to the max magnitude
+    assert errs["dw"] < 1e-3, errs                            # fp32 result of exact bf16 products
+
+
+@pytest.mark.parametrize("c,with_res,relu", [(32, False, True), (96, True, True), (256, True, False)])
+def test_bn_act_bf16_matches_torch(cuda_lib, c, with_res, relu):
+    """Fused BatchNorm + residual + ReLU on bf16 features (fp32 statistics / parameters) against fp64 torch on the same
+    bf16-rounded inputs: outputs and input gradients to bf16 rounding, parameter gradients and statistics to 1e-3."""
+    from ponderv2_b200.bn_act import bn_act
+    dev = _dev()
+    torch.manual_seed(c)
+    n = 5003
+    x = (torch.randn(n, c, device=dev) * 2 + 0.5).to(torch.bfloat16)
+    res = torch.randn(n, c, device=dev).to(torch.bfloat16) if with_res else None
+    g = torch.randn(n, c, device=dev).to(torch.bfloat16)
+    bn = torch.nn.BatchNorm1d(c, eps=1e-3, momentum=0.01).to(dev).train()
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5); bn.bias.normal_()
+    ref = torch.nn.BatchNorm1d(c, eps=1e-3, momentum=0.01).double().train()
+    ref.load_state_dict({k: v.detach().cpu().double() if v.is_floating_point() else v.cpu() for k, v in bn.state_dict().items()})
+    xg = x.clone().requires_grad_(True)
+    rg = res.clone().requires_grad_(True) if with_res else None
+    y = bn_act(xg, bn, rg, relu)
+    assert y.dtype == torch.bfloat16
+    y.backward(g)
+    xr = x.cpu().double().requires_grad_(True)
+    rr = res.cpu().double().requires_grad_(True) if with_res else None
+    yr = ref(xr)
+    if with_res:
+        yr = yr + rr
+    if relu:
+        yr = torch.relu(yr)
+    # the kernel applies the ReLU mask from its own bf16 output; compare away from the kink
+    yr.backward(g.cpu().double())
+    sc = lambda t: max(t.abs().max().item(), 1e-6)
+    assert (y.detach().cpu().double() - yr.detach()).abs().max().item() < 1e-2 * sc(yr)
+    far = (yr.detach().abs() > 0.05) | (not relu)
+    assert ((xg.grad.cpu().double() - xr.grad).abs() * far).max().item() < 2e-2 * sc(xr.grad)
+    if with_res:
+        assert ((rg.grad.cpu().double() - rr.grad).abs() * far).max().item() < 2e-2 * sc(rr.grad)
+    assert (bn.weight.grad.cpu().double() - ref.weight.grad).abs().max().item() < 2e-2 * sc(ref.weight.grad)
+    assert (bn.bias.grad.cpu().double() - ref.bias.grad).abs().max().item() < 2e-2 * sc(ref.bias.grad)
+    assert (bn.running_mean.cpu().double() - ref.running_mean).abs().max().item() < 1e-4
+    assert (bn.running_var.cpu().double() - ref.running_var).abs().max().item() < 1e-4 * sc(ref.running_var)
+
+
+def test_spunet_backbone_bf16_matches_oracle(cuda_lib):
+    """Whole SpUNet-v1m1 under bf16 autocast (BASELINE configs[2]'s dtype; the reference runs fp16 autocast) on an
+    8 k-voxel batch against the fp64 oracle with the same fp32 master weights: features to bf16-chain accuracy, the
+    parameter gradients jointly."""
+    from ponderv2_b200.backbone import SpUNetBase
+    from tests.conftest import record
+    dev = _dev()
+    torch.manual_seed(0)
+    a, b = synth.indoor_cloud(4800, 21), synth.indoor_cloud(3200, 22)
+    gc = np.concatenate([a["grid_coord"], b["grid_coord"]])
+    feat = np.concatenate([a["feat"], b["feat"]])
+    offset = np.array([4800, 8000], dtype=np.int64)
+    model = SpUNetBase(in_channels=6, num_classes=0).to(dev).train()
+    sd = {k: v.detach().cpu().double() for k, v in model.state_dict().items()}
+    for k, v in sd.items():
+        if v.is_floating_point() and ("weight" in k or "bias" in k):
+            v.requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out = model({"grid_coord": torch.from_numpy(gc).to(dev), "feat": torch.from_numpy(feat).to(dev),
+                     "offset": torch.from_numpy(offset).to(dev)})
+    assert out.dtype == torch.bfloat16
+    ref = so.spunet_forward(sd, gc, torch.from_numpy(feat).double(), offset)
+    err = (out.detach().cpu().double() - ref.detach()).abs().max().item() / ref.abs().max().item()
+    rel_l2 = ((out.detach().cpu().double() - ref.detach()).norm() / ref.detach().norm()).item()
+    g = torch.randn(ref.shape, dtype=torch.float64, generator=torch.Generator().manual_seed(1))
+    ref.backward(g)
+    out.backward(g.to(dev, torch.bfloat16))
+    num = den = 0.0
+    for name, p in model.named_parameters():
+        rg = sd[name].grad
+        d = (p.grad.cpu().double() - rg)
+        num += d.pow(2).sum().item(); den += rg.pow(2).sum().item()
+    joint = (num / den) ** 0.5
+    record("spunet_backbone_bf16_matches_oracle", fwd_max=err, fwd_l2=rel_l2, grad_joint=joint)
+    # 59 layers of bf16 storage: each layer rounds to 2^-8; errors accumulate like a random walk through the depth
+    assert rel_l2 < 3e-2, rel_l2
+    assert err < 0.15, err
+    assert joint < 0.15, joint
 
 
 # ------------------------------------------------------------------------------------------ dense linear (render MLP)
