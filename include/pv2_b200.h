@@ -164,9 +164,9 @@ int pv2_bn_act_bwd_t(const void* x, const void* dy, const void* y, const float* 
  * ------------------------------------------------------------------------------------------ */
 int pv2_densify_fwd(const float* feat, const int64_t* cell, int64_t n, int c, int64_t cells,
                     float* volume, int32_t* count, void* stream);
-/* dfeat[i,:] = dvolume[cell[i],:] / count[cell[i]] */
+/* dfeat[i,:] = dvolume[cell[i],:] / count[cell[i]]  (0 for cell[i] outside [0, cells), as the forward drops them) */
 int pv2_densify_bwd(const float* dvolume, const int64_t* cell, const int32_t* count, int64_t n,
-                    int c, float* dfeat, void* stream);
+                    int c, int64_t cells, float* dfeat, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Trilinear sampler with first and second derivatives (B2).  Same argument meaning as

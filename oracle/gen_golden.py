@@ -217,6 +217,124 @@ def gen_spunet_state() -> None:
     print(f"spunet_v1m1_state: {len(state)} entries, {n_conv} conv parameters")
 
 
+def gen_rayprep_case() -> None:
+    """Golden vectors of the indoor ray preparation: the reference's own `PonderIndoor.to_unit_cube`, `ray_sample` and
+    `grid_sample` (ponder_indoor_base.py:344-633) run on a small synthetic collate dict (2 scenes, 2 views of 12 x 16
+    pixels), with `torch.randperm` recorded so that the product can be handed the same pixel choice."""
+    from ponder.models.ponder.ponder_indoor_base import PonderIndoor
+
+    g = torch.Generator().manual_seed(77)
+    B, V, H, W, n = 2, 2, 12, 16, 24
+    counts = [700, 500]
+    coord = torch.cat([torch.rand(c, 3, generator=g) * torch.tensor([4.0, 3.0, 2.5]) + torch.tensor([1.0, -2.0, 0.3])
+                       for c in counts])
+    offset = torch.tensor(counts).cumsum(0)
+    depth = torch.rand(B, V, H, W, generator=g) * 3.0 + 0.5
+    depth[torch.rand(B, V, H, W, generator=g) < 0.2] = 0.0            # invalid pixels
+    rgb = torch.rand(B, V, H, W, 3, generator=g)
+    fx = 14.0
+    intrinsic = torch.tensor([[fx, 0.0, (W - 1) / 2, 0.0], [0.0, fx, (H - 1) / 2, 0.0], [0.0, 0.0, 1.0, 0.0],
+                              [0.0, 0.0, 0.0, 1.0]]).repeat(B, 1, 1)
+    extrinsic = torch.zeros(B, V, 4, 4)
+    for b in range(B):
+        for v in range(V):
+            a = torch.randn(3, 3, generator=g)
+            q, _ = torch.linalg.qr(a)
+            if torch.det(q) < 0:
+                q[:, 0] = -q[:, 0]
+            extrinsic[b, v, :3, :3] = q
+            extrinsic[b, v, :3, 3] = torch.randn(3, generator=g) * 0.5 + torch.tensor([0.0, 0.0, 2.0])
+            extrinsic[b, v, 3, 3] = 1.0
+    depth_scale = torch.tensor([1.0, 0.5])
+    dd = dict(coord=coord.clone(), offset=offset.clone(), rgb=rgb.clone(), depth=depth.clone(), intrinsic=intrinsic.clone(),
+              extrinsic=extrinsic.clone(), depth_scale=depth_scale.clone())
+    me = object.__new__(PonderIndoor)
+    padding = 0.1
+    object.__setattr__(me, "bounds", np.array([[-0.5 - padding / 2] * 3, [0.5 + padding / 2] * 3], dtype=np.float32))
+    object.__setattr__(me, "ray_nsample", n)
+    object.__setattr__(me, "render_semantic", False)
+    object.__setattr__(me, "grid_size", 0.02)
+    perms = []
+    orig = torch.randperm
+
+    def fake(nn_, *a, **k):
+        t = orig(nn_, generator=g)
+        perms.append(t.clone())
+        return t
+    torch.randperm = fake
+    try:
+        d1 = PonderIndoor.to_unit_cube(me, dd)
+        ray = PonderIndoor.ray_sample(me, d1)
+    finally:
+        torch.randperm = orig
+    d2 = PonderIndoor.grid_sample(me, {k: (v.clone() if torch.is_tensor(v) else v) for k, v in d1.items()})
+    # the pixels the reference picked, as flat indices y * W + x per (scene, view)
+    pix = torch.zeros(B, V, n, dtype=torch.int64)
+    it = iter(perms)
+    for b in range(B):
+        for v in range(V):
+            ys, xs = torch.where((depth[b, v] > 0).float() > 0)
+            sel = next(it)[:n]
+            pix[b, v] = ys[sel] * W + xs[sel]
+    arrays = {"in.coord": coord, "in.offset": offset, "in.rgb": rgb, "in.depth": depth, "in.intrinsic": intrinsic,
+              "in.extrinsic": extrinsic, "in.depth_scale": depth_scale, "pixels": pix,
+              "cube.coord": d1["coord"], "cube.extrinsic": d1["extrinsic"], "cube.depth_scale": d1["depth_scale"],
+              "cube.pc_scale": d1["pc_scale"], "cube.bbox": d1["bbox"],
+              "grid.bbox": d2["bbox"], "grid.resolution": d2["resolution"],
+              "ray.ray_o": ray["ray_o"], "ray.ray_d": ray["ray_d"], "ray.rgb": ray["rgb"], "ray.depth": ray["depth"]}
+    np.savez_compressed(GOLD / "rayprep_indoor.npz", meta=json.dumps(dict(B=B, V=V, H=H, W=W, n=n, padding=padding,
+                                                                            grid_size=0.02)),
+                        **{k: v.numpy() for k, v in arrays.items()})
+    print(f"rayprep_indoor: {len(arrays)} arrays, rays {tuple(ray['ray_o'].shape)}, hit fraction "
+          f"{float((ray['depth'] > 0).float().mean()):.2f}")
+
+
+INDOOR_MODEL_CFG = dict(
+    type="PonderIndoor-v2",
+    backbone=dict(type="SpUNet-v1m1", in_channels=6, num_classes=0, channels=(32, 64, 128, 256, 256, 128, 96, 96),
+                  layers=(2, 3, 4, 6, 2, 2, 2, 2)),
+    projection=dict(type="UNet3D-v1m2", in_channels=96, out_channels=128),
+    mask=dict(ratio=0.8, size=8, channel=6), grid_shape=(128, 128, 32), grid_size=0.02, val_ray_split=10240,
+    ray_nsample=256, padding=0.1, pool_type="mean", render_semantic=False, conditions=("ScanNet",))
+OUTDOOR_MODEL_CFG = dict(
+    type="PonderOutdoor-v2", mask=dict(ratio=0.8, size=8, channel=4),
+    backbone=dict(type="SpUNet-v1m1", in_channels=4, num_classes=0, channels=(32, 64, 128, 256, 256, 128, 96, 96),
+                  layers=(2, 3, 4, 6, 2, 2, 2, 2)),
+    projection=dict(type="SimpleConv3D-v1m1", in_channels=96, out_channels=32),
+    scene_bbox=((-54.0, -54.0, -5.0, 54.0, 54.0, 3.0),), grid_shape=((180, 180, 5),), grid_size=((0.6, 0.6, 1.6),),
+    val_ray_split=8192, pool_type="mean", share_volume=True, render_semantic=False, conditions=("nuScenes",))
+
+
+def gen_model_contracts(Dict) -> None:
+    """(1) UNet3D-v1m2 (ponder/models/ponder/unet3d.py:710): a tiny instance's parameters, an input and the reference's
+    output (pure torch, CPU).  (2) state_dict names + shapes of the reference's PonderIndoor-v2 / PonderOutdoor-v2 built
+    from config dicts through the reference registry (spconv aliased to ponderv2_b200.spconv for construction only)."""
+    from ponder.models.builder import build_model
+    from ponder.models.ponder.unet3d import UNet3Dv1m2
+    import ponder.models.ponder  # noqa: F401  registers PonderIndoor-v2 / PonderOutdoor-v2
+
+    torch.manual_seed(3)
+    net = UNet3Dv1m2(in_channels=8, out_channels=6, f_maps=4, num_levels=3).train()
+    x = torch.randn(2, 8, 8, 12, 8)
+    sd0 = {k: v.clone() for k, v in net.state_dict().items()}
+    y = net(x)
+    y.square().mean().backward()
+    arrays = {"x": x, "y": y.detach()}
+    for k, v in sd0.items():
+        arrays["param." + k] = v
+    for k, p_ in net.named_parameters():
+        arrays["grad." + k] = p_.grad
+    np.savez_compressed(GOLD / "unet3d_v1m2.npz", **{k: v.numpy() for k, v in arrays.items()})
+    contracts = {}
+    for name, cfg, rk, s0, si in (("PonderIndoor-v2", INDOOR_MODEL_CFG, "indoor", 96, 36),
+                                  ("PonderOutdoor-v2", OUTDOOR_MODEL_CFG, "outdoor", 72, 24)):
+        c = Dict(dict(cfg, renderer=renderer_cfg(rk, s0, si, Dict)))
+        m = build_model(c)
+        contracts[name] = {k: list(v.shape) for k, v in m.state_dict().items()}
+    (GOLD / "ponder_models_state.json").write_text(json.dumps(contracts, indent=0))
+    print("model contracts:", {k: len(v) for k, v in contracts.items()}, "| unet3d params", len(sd0))
+
+
 def main() -> None:
     GOLD.mkdir(parents=True, exist_ok=True)
     Dict = _install_stubs()
@@ -227,6 +345,10 @@ def main() -> None:
         gen_render_case(name, spec, Dict)
     if not only or "spunet_state" in only:
         gen_spunet_state()
+    if not only or "rayprep" in only:
+        gen_rayprep_case()
+    if not only or "models" in only:
+        gen_model_contracts(Dict)
 
 
 if __name__ == "__main__":

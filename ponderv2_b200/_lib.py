@@ -65,7 +65,7 @@ SIGNATURES = {
                                  _vp]),
     "pv2_bn_act_bwd_t": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _i64, _int, _vp, _vp, _vp, _vp, _int, _vp, _sz, _vp]),
     "pv2_densify_fwd": (_int, [_vp, _vp, _i64, _int, _i64, _vp, _vp, _vp]),
-    "pv2_densify_bwd": (_int, [_vp, _vp, _vp, _i64, _int, _vp, _vp]),
+    "pv2_densify_bwd": (_int, [_vp, _vp, _vp, _i64, _int, _i64, _vp, _vp]),
     "pv2_trilinear_fwd": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _int, _int, _int, _int, _vp]),
     "pv2_trilinear_bwd": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _int, _int, _int, _int, _vp]),
     "pv2_trilinear_bwd_bwd": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64,

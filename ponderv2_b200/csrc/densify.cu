@@ -63,7 +63,8 @@ __global__ void scatter_mean_scalar_kernel(const float* __restrict__ feat, const
 }
 
 __global__ void gather_mean_kernel(const float* __restrict__ dvolume, const int64_t* __restrict__ cell,
-                                   const int32_t* __restrict__ count, int64_t n, int ch, float* __restrict__ dfeat) {
+                                   const int32_t* __restrict__ count, int64_t n, int ch, int64_t cells,
+                                   float* __restrict__ dfeat) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t total = n * ch;
@@ -72,7 +73,7 @@ __global__ void gather_mean_kernel(const float* __restrict__ dvolume, const int6
     int g = (int)(idx - i * ch);
     int64_t c = __ldg(&cell[i]);
     float v = 0.f;
-    if (c >= 0) v = __ldg(&dvolume[c * ch + g]) / (float)__ldg(&count[c]);
+    if (c >= 0 && c < cells) v = __ldg(&dvolume[c * ch + g]) / (float)__ldg(&count[c]);   // same bounds as the forward
     dfeat[idx] = v;
   }
 }
@@ -101,12 +102,12 @@ int pv2_densify_fwd(const float* feat, const int64_t* cell, int64_t n, int c, in
   PV2_DONE(3);
 }
 
-int pv2_densify_bwd(const float* dvolume, const int64_t* cell, const int32_t* count, int64_t n, int c, float* dfeat,
-                    void* stream_) {
-  PV2_CHECK_ARG(n >= 0 && c > 0);
+int pv2_densify_bwd(const float* dvolume, const int64_t* cell, const int32_t* count, int64_t n, int c, int64_t cells,
+                    float* dfeat, void* stream_) {
+  PV2_CHECK_ARG(n >= 0 && c > 0 && cells >= 0);
   if (n == 0) return 0;
   PV2_CHECK_ARG(dvolume && cell && count && dfeat);
-  gather_mean_kernel<<<pv2_grid_for(n * c, 256), 256, 0, (cudaStream_t)stream_>>>(dvolume, cell, count, n, c, dfeat);
+  gather_mean_kernel<<<pv2_grid_for(n * c, 256), 256, 0, (cudaStream_t)stream_>>>(dvolume, cell, count, n, c, cells, dfeat);
   PV2_DONE(1);
 }
 

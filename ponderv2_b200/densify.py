@@ -41,8 +41,8 @@ class _DensifyFunction(torch.autograd.Function):
         dvolume = dvolume.contiguous()
         dfeat = torch.empty((n, c), dtype=torch.float32, device=dvolume.device)
         with torch.cuda.device(dvolume.device):
-            _lib.check(lib.pv2_densify_bwd(_lib.ptr(dvolume), _lib.ptr(cell), _lib.ptr(count), n, c, _lib.ptr(dfeat),
-                                           _lib.stream_ptr()), "pv2_densify_bwd")
+            _lib.check(lib.pv2_densify_bwd(_lib.ptr(dvolume), _lib.ptr(cell), _lib.ptr(count), n, c, count.shape[0],
+                                           _lib.ptr(dfeat), _lib.stream_ptr()), "pv2_densify_bwd")
         return dfeat, None, None
 
 
@@ -58,6 +58,12 @@ def indoor_cells(coord: torch.Tensor, batch: torch.Tensor, resolution: torch.Ten
     """Cell id per voxel, pooling branch of ponder_indoor_base.py:199-213.
     coord [N,3] float (scene frame), batch [N] int64, resolution [B] (voxels along the longest bbox edge)."""
     gs = torch.tensor([float(g) for g in grid_shape], dtype=torch.float32, device=coord.device)
+    if coord.is_cuda:
+        # only the pooling branch of PonderIndoor.to_dense is implemented (every scene whose longest edge covers the grid,
+        # ponder_indoor_base.py:199-216); smaller scenes take the reference's trilinear-upsample branch (:217-330).
+        # Checked on the device without a host sync: a violation raises a CUDA device-side assertion.
+        torch._assert_async((resolution.to(coord.device) + 1 >= min(int(g) for g in grid_shape)).all(),
+                            "densify.indoor_cells: scene resolution below min(grid_shape): the reference would upsample")
     v = torch.floor_divide(coord, grid_size).int()                       # (coord // grid_size).int()
     cur = (resolution.to(coord.device)[batch] + 1).to(torch.int64)       # int(resolution + 1)
     scale = cur.to(torch.float32)[:, None] / gs[None, :]                 # current_resolution / FloatTensor(grid_shape)

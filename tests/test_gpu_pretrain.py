@@ -268,3 +268,75 @@ def test_outdoor_block_masking(cuda_lib):
     keep_vox = torch.from_numpy(keep_blk[inv.reshape(-1)])
     want = torch.where(keep_vox[:, None], feat, model.mtoken.detach().cpu().expand_as(feat))
     assert torch.equal(got, want)
+
+
+def test_ponder_indoor_v2_from_collate_dict(cuda_lib):
+    """`MODELS.build(dict(type="PonderIndoor-v2", ...))` with the ScanNet config's projection (UNet3D-v1m2) on the collate
+    dict the reference dataloader produces (coord / grid_coord / feat / offset + rgb, depth, intrinsic, extrinsic,
+    depth_scale): one training step runs end to end on the device, and its loss equals the same model fed with rays
+    prepared by ponderv2_b200.rayprep on the CPU (the formulation pinned against the reference's ray_sample in
+    tests/test_host_cpu.py) -- i.e. device ray preparation and the adapter wiring add nothing of their own."""
+    from ponderv2_b200 import rayprep
+    from ponderv2_b200.models import MODELS
+    dev = torch.device("cuda:0")
+    torch.manual_seed(4)
+    B, V, H, W, n = 2, 2, 20, 28, 24
+    clouds = [synth.indoor_cloud(2500, 51), synth.indoor_cloud(1800, 52)]
+    coord = torch.cat([torch.from_numpy(c["coord"]) + torch.tensor([1.0, 2.0, 0.5]) for c in clouds])
+    gc = torch.cat([torch.from_numpy(c["grid_coord"]) for c in clouds])
+    feat = torch.cat([torch.from_numpy(c["feat"]) for c in clouds])
+    offset = torch.tensor([2500, 4300])
+    g = torch.Generator().manual_seed(8)
+    depth = torch.rand(B, V, H, W, generator=g) * 2.0 + 0.5
+    depth[torch.rand(B, V, H, W, generator=g) < 0.15] = 0.0
+    rgb = torch.rand(B, V, H, W, 3, generator=g)
+    intrinsic = torch.tensor([[30.0, 0, (W - 1) / 2, 0], [0, 30.0, (H - 1) / 2, 0], [0, 0, 1, 0], [0, 0, 0, 1.0]]).repeat(B, 1, 1)
+    extrinsic = torch.zeros(B, V, 4, 4)
+    for b in range(B):
+        ctr = coord[(0 if b == 0 else 2500):(2500 if b == 0 else 4300)].mean(0)
+        for v in range(V):
+            q, _ = torch.linalg.qr(torch.randn(3, 3, generator=g))
+            if torch.det(q) < 0:
+                q[:, 0] = -q[:, 0]
+            extrinsic[b, v, :3, :3] = q
+            extrinsic[b, v, :3, 3] = -(q @ ctr) + torch.tensor([0.0, 0.0, 0.3])     # camera near the scene centre
+            extrinsic[b, v, 3, 3] = 1.0
+    collate = dict(coord=coord, grid_coord=gc, feat=feat, offset=offset, rgb=rgb, depth=depth, intrinsic=intrinsic,
+                   extrinsic=extrinsic, depth_scale=torch.ones(B), condition=["ScanNet"] * B)
+    cfg = dict(type="PonderIndoor-v2",
+               backbone=dict(type="SpUNet-v1m1", in_channels=6, num_classes=0),
+               projection=dict(type="UNet3D-v1m2", in_channels=96, out_channels=128, f_maps=8, num_levels=3),
+               renderer=_renderer_cfg(24, 8), mask=None, grid_shape=(32, 32, 16), grid_size=0.02, ray_nsample=n,
+               padding=0.1, render_semantic=False, conditions=("ScanNet",))
+    model = MODELS.build(cfg).to(dev).train()
+    pixels = rayprep.sample_pixels(depth, n, keys=torch.rand(B, V, H * W, generator=g))
+    R = V * n
+    noise_cpu = {"uniform": torch.rand(R, 25, generator=g), "pdf": torch.rand(R, 9, generator=g)}
+
+    def run(prepared_on_cpu: bool):
+        torch.manual_seed(0)
+        for m in model.modules():                       # same BatchNorm running state for both runs is irrelevant in train mode
+            pass
+        noise = {k: v.to(dev) for k, v in noise_cpu.items()}
+        dd = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in collate.items()}
+        if not prepared_on_cpu:
+            noise["pixels"] = pixels.to(dev)
+            return model(dd, noise=noise)
+        cube = rayprep.to_unit_cube({k: v for k, v in collate.items() if torch.is_tensor(v)})
+        ray = rayprep.ray_sample(cube, n, model.bounds, pixels=pixels)
+        cube = rayprep.grid_sample(cube, model.grid_size)
+        step_in = dict(dd)
+        step_in.update({k: cube[k].to(dev) for k in ("coord", "resolution")})
+        step_in.update({k: v.to(dev) for k, v in ray.items()})
+        step_in["sparse_backbone_feat"] = model.backbone(dd)
+        return model.forward_after_backbone(step_in, noise)
+
+    out_dev = run(False)
+    out_dev["loss"].backward()
+    assert all(torch.isfinite(v).all() for v in out_dev.values())
+    n_grad = sum(p.grad is not None and bool(torch.isfinite(p.grad).all()) for p in model.parameters())
+    assert n_grad > 150
+    out_cpu = run(True)
+    for k in out_dev:
+        a, b_ = out_dev[k].item(), out_cpu[k].item()
+        assert abs(a - b_) < 2e-4 * max(1.0, abs(b_)), (k, a, b_)
