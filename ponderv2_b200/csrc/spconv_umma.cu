@@ -1345,6 +1345,8 @@ int launch(const GGParams& p0, cudaStream_t stream) {
   if (kSplit && !p.y_split && p.act == 0 && tiles * 2 <= PV2_SM_COUNT && p.num_chunks >= 16) {  // (act: one writer per row)
     ksplit = (PV2_SM_COUNT + (int)tiles - 1) / (int)tiles;  // ~one CTA per SM in total
     if (ksplit > p.num_chunks / 8) ksplit = p.num_chunks / 8;
+    const int cap = pv2_get_option("gg_ksplit_max");
+    if (cap > 0 && ksplit > cap) ksplit = cap;
     if (ksplit < 1) ksplit = 1;
   }
   p.ksplit = ksplit;

@@ -66,6 +66,7 @@ class FlatParameters:
             p.data = view
             gview = self.flat_grad[o:o + n].view(p.shape)
             p.grad = gview
+            p._pv2_sink = (self, gview)     # kernels that can accumulate in place write here (spconv/pytorch.py)
             self._views.append(gview)
         self.module = module
         self.master = nn.Parameter(self.flat_param, requires_grad=True)
@@ -89,6 +90,7 @@ class FlatParameters:
         self._comm_stream = None
         self._works = []
         self._launched = [False] * len(self.chunks)
+        self._aux_streams = []  # side streams that write gradients straight into the buffer
         self._frozen = None     # (indices, saved values) of parameters that never get a gradient
         self._steps = 0
 
@@ -129,8 +131,19 @@ class FlatParameters:
         opt.register_step_post_hook(lambda *_: flat._after_step())
         return opt
 
+    def note_aux_stream(self, stream) -> None:
+        """A side stream is writing gradients into the buffer; the all-reduce and the optimizer wait for it."""
+        if stream not in self._aux_streams:
+            self._aux_streams.append(stream)
+
+    def _join_aux(self, waiter) -> None:
+        for s in self._aux_streams:
+            waiter.wait_stream(s)
+
     def _before_step(self) -> None:
         self.sync_grads()
+        if self.flat_grad.is_cuda:
+            self._join_aux(torch.cuda.current_stream(self.flat_grad.device))
         self.wait_all_reduce()
 
     def _after_step(self) -> None:
@@ -157,10 +170,14 @@ class FlatParameters:
         whole buffer; with it, only the slices whose completion hook has not fired yet are reduced here and the
         launching stream then waits for the side stream."""
         self.sync_grads()
+        if self.flat_grad.is_cuda:
+            self._join_aux(torch.cuda.current_stream(self.flat_grad.device))
         if not _is_dist(group):
             return
         if not self._overlap:
-            self._reduce(self.flat_grad, group)
+            w = self._reduce(self.flat_grad, group)
+            if w is not None:
+                w.wait()          # stream-ordered: the launching stream waits for NCCL's
             return
         for c in range(len(self.chunks)):
             if not self._launched[c]:
@@ -211,6 +228,7 @@ class FlatParameters:
         view = self.flat_grad[s:e]
         if self._comm_stream is not None:
             self._comm_stream.wait_stream(torch.cuda.current_stream(self.flat_grad.device))
+            self._join_aux(self._comm_stream)
             with torch.cuda.stream(self._comm_stream):
                 w = self._reduce(view, group)
         else:

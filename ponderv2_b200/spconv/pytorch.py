@@ -184,11 +184,24 @@ def _gather_gemm(x: torch.Tensor, w3: torch.Tensor, bias: Optional[torch.Tensor]
     return y
 
 
-def _wgrad(x: torch.Tensor, dy: torch.Tensor, tmap: TileMap, kvol: int) -> torch.Tensor:
+_WGRAD_STREAMS = {}
+
+
+def _wgrad_stream(dev: torch.device) -> "torch.cuda.Stream":
+    """Side stream for weight gradients written straight into a flat gradient buffer (see _SparseConvFunction.backward)."""
+    key = (dev.type, dev.index)
+    if key not in _WGRAD_STREAMS:
+        _WGRAD_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _WGRAD_STREAMS[key]
+
+
+def _wgrad(x: torch.Tensor, dy: torch.Tensor, tmap: TileMap, kvol: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dw[co, k, ci] += sum_j dy[j, co] x[nbr[k][j], ci].  `out` (fp32 [cout, kvol, cin], contiguous) is accumulated into;
+    without it a zeroed tensor is allocated."""
     nbr, order = tmap.nbr, tmap.order
     lib = _lib.load()
     cin, cout = x.shape[1], dy.shape[1]
-    dw = torch.zeros((cout, kvol, cin), dtype=torch.float32, device=x.device)
+    dw = out if out is not None else torch.zeros((cout, kvol, cin), dtype=torch.float32, device=x.device)
     b = x.element_size()
     nbytes = x.shape[0] * cin * b + dy.shape[0] * cout * b + kvol * cin * cout * 4 + 4 * kvol * dy.shape[0]
     ws_bytes = lib.pv2_wgrad_workspace_bytes(x.shape[0], dy.shape[0], cin, cout) if x.dtype == torch.float32 else 0
@@ -226,6 +239,13 @@ class _SparseConvFunction(torch.autograd.Function):
         w3 = weight.reshape(cout, -1, cin).to(compute_dtype)
         b = bias.float() if bias is not None else None
         y = _gather_gemm(xc, w3, b, map_fwd, n_out)
+        # A parameter re-homed by ponderv2_b200.dist.FlatParameters carries a view of the flat fp32 gradient buffer: the
+        # weight-gradient kernel then accumulates straight into it (no zero-filled temporary, no autograd accumulation
+        # kernel) on a side stream, off the critical path of the data gradients.
+        sink = getattr(weight, "_pv2_sink", None)
+        ctx.sink = sink if (sink is not None and cin == ctx.cin_orig and sink[1].dtype == torch.float32
+                            and sink[1].is_contiguous() and sink[1].numel() == weight.numel()) else None
+        ctx.param = weight if ctx.sink is not None else None
         ctx.save_for_backward(xc, w3)
         ctx.map_fwd, ctx.map_bwd = map_fwd, map_bwd
         ctx.flip = flip
@@ -249,7 +269,17 @@ class _SparseConvFunction(torch.autograd.Function):
                                                         int(ctx.flip), _lib.dtype_code(w3.dtype), _lib.stream_ptr()),
                            "pv2_spconv_dgrad_weights")
             dx = _gather_gemm(dy, wt, None, ctx.map_bwd, xc.shape[0]).to(ctx.x_dtype)[:, :ctx.cin_orig]
-        if ctx.needs_input_grad[1]:
+        if ctx.needs_input_grad[1] and ctx.sink is not None:
+            flat, view = ctx.sink
+            cur = torch.cuda.current_stream(dy.device)
+            side = _wgrad_stream(dy.device)
+            side.wait_stream(cur)                       # dy (and, earlier, xc) are produced on the launching stream
+            with torch.cuda.stream(side):
+                _wgrad(xc, dy, ctx.map_fwd, w3.shape[1], out=view.view(w3.shape[0], w3.shape[1], w3.shape[2]))
+            xc.record_stream(side); dy.record_stream(side)
+            flat.note_aux_stream(side)                  # optimizer / all-reduce wait for it
+            flat.mark_ready(ctx.param)
+        elif ctx.needs_input_grad[1]:
             dw = _wgrad(xc, dy, ctx.map_fwd, w3.shape[1]).reshape(ctx.weight_shape).to(ctx.weight_dtype)[..., :ctx.cin_orig]
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = dy.float().sum(0)

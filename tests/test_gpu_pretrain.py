@@ -340,3 +340,39 @@ def test_ponder_indoor_v2_from_collate_dict(cuda_lib):
     for k in out_dev:
         a, b_ = out_dev[k].item(), out_cpu[k].item()
         assert abs(a - b_) < 2e-4 * max(1.0, abs(b_)), (k, a, b_)
+
+
+def test_flat_buffer_sink_gradients_match_autograd(cuda_lib):
+    """With FlatParameters the sparse-conv weight gradients are accumulated by the kernel straight into the flat buffer
+    on a side stream (spconv/pytorch.py `_pv2_sink`); they must equal the gradients autograd collects without it, and two
+    optimizer steps must leave identical weights."""
+    from ponderv2_b200.backbone import SpUNetBase
+    from ponderv2_b200.dist import FlatParameters
+    dev = torch.device("cuda:0")
+    cloud = synth.indoor_cloud(6000, 77)
+    inp = {k: torch.from_numpy(cloud[k]).to(dev) for k in ("grid_coord", "feat", "offset")}
+    torch.manual_seed(1)
+    m1 = SpUNetBase(in_channels=6, num_classes=0).to(dev).train()
+    torch.manual_seed(1)
+    m2 = SpUNetBase(in_channels=6, num_classes=0).to(dev).train()
+    flat = FlatParameters(m2)
+    o1 = torch.optim.SGD(m1.parameters(), lr=0.05, momentum=0.9)
+    o2 = flat.make_optimizer(torch.optim.SGD, lr=0.05, momentum=0.9)
+    g = torch.randn(6000, 96, device=dev)
+    for step in range(2):
+        o1.zero_grad(); o2.zero_grad()
+        (m1(dict(inp)) * g).sum().backward()
+        (m2(dict(inp)) * g).sum().backward()
+        flat.all_reduce_mean()          # joins the side stream
+        torch.cuda.synchronize()
+        if step == 0:
+            worst = 0.0
+            for (n1, p1), (n2, p2) in zip(m1.named_parameters(), m2.named_parameters()):
+                assert n1 == n2 and p2.grad.data_ptr() >= flat.flat_grad.data_ptr()
+                e = (p1.grad - p2.grad).norm().item() / max(p1.grad.norm().item(), 1e-12)
+                worst = max(worst, e)
+            assert worst < 1e-4, worst     # same kernels; only the order of the fp32 atomics differs
+        o1.step(); o2.step()
+    torch.cuda.synchronize()
+    for p1, p2 in zip(m1.parameters(), m2.parameters()):
+        assert (p1 - p2).abs().max().item() < 1e-4 * max(1.0, p1.abs().max().item())
