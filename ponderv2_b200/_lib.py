@@ -165,8 +165,37 @@ class _Profile:
 PROFILE = _Profile()
 
 
-class timed:
+class _NullCtx:
+    __slots__ = ()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NULL = _NullCtx()
+
+
+def on_device(dev):
+    """`with on_device(t.device):` — torch.cuda.device(dev) only when `dev` is not already current (the context manager
+    costs two driver calls per entry; the wrappers are entered ~1000 times per step)."""
+    import torch
+    if dev.index is None or torch.cuda.current_device() == dev.index:
+        return _NULL
+    return torch.cuda.device(dev)
+
+
+def timed(name, nbytes=0, flops=0):
     """with timed("pv2_x", bytes, flops): <C-ABI call>  — records CUDA events on the launching stream when enabled."""
+    if PROFILE.enabled_for is None or name not in PROFILE.enabled_for:
+        return _NULL
+    return _Timed(name, nbytes, flops)
+
+
+class _Timed:
+    """CUDA-event pair around one C-ABI call (bench.py's instrumented loop)."""
 
     __slots__ = ("name", "nbytes", "flops", "e0")
 

@@ -28,7 +28,7 @@ def make_sparse_indices(grid_coord: torch.Tensor, offset: torch.Tensor) -> torch
     gc = grid_coord.contiguous().long()
     off = offset.contiguous().long()
     out = torch.empty((n, 4), dtype=torch.int32, device=gc.device)
-    with torch.cuda.device(gc.device):
+    with _lib.on_device(gc.device):
         _lib.check(lib.pv2_make_indices(_lib.ptr(gc), _lib.ptr(off), n, off.shape[0], _lib.ptr(out),
                                         _lib.stream_ptr()), "pv2_make_indices")
     return out

@@ -26,7 +26,7 @@ class _DensifyFunction(torch.autograd.Function):
         n, c = feat.shape
         volume = torch.empty((cells_total, c), dtype=torch.float32, device=feat.device)
         count = torch.empty(cells_total, dtype=torch.int32, device=feat.device)
-        with torch.cuda.device(feat.device):
+        with _lib.on_device(feat.device):
             _lib.check(lib.pv2_densify_fwd(_lib.ptr(feat), _lib.ptr(cell), n, c, cells_total, _lib.ptr(volume),
                                            _lib.ptr(count), _lib.stream_ptr()), "pv2_densify_fwd")
         ctx.save_for_backward(cell, count)
@@ -40,7 +40,7 @@ class _DensifyFunction(torch.autograd.Function):
         lib = _lib.load()
         dvolume = dvolume.contiguous()
         dfeat = torch.empty((n, c), dtype=torch.float32, device=dvolume.device)
-        with torch.cuda.device(dvolume.device):
+        with _lib.on_device(dvolume.device):
             _lib.check(lib.pv2_densify_bwd(_lib.ptr(dvolume), _lib.ptr(cell), _lib.ptr(count), n, c, count.shape[0],
                                            _lib.ptr(dfeat), _lib.stream_ptr()), "pv2_densify_bwd")
         return dfeat, None, None

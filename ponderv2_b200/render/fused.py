@@ -28,7 +28,7 @@ def _linear(x, x_row, x_lo, presplit, w, bias, y, y_row, y_lo, y_split, act, y2,
     ws_bytes = lib.pv2_linear_workspace_bytes(rows, cin, cout, int(presplit))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=w.device)
     w = w.contiguous()
-    with torch.cuda.device(w.device):
+    with _lib.on_device(w.device):
         _lib.check(lib.pv2_linear(_lib.C.c_void_p(x.data_ptr()), x_row, x_lo, int(presplit), _lib.ptr(w),
                                   _lib.ptr(bias.contiguous()) if bias is not None else None,
                                   _lib.C.c_void_p(y.data_ptr()), y_row, y_lo, int(y_split), act,
@@ -41,7 +41,7 @@ def _dense_wgrad(x, x_row, x_lo, dy, dy_row, dy_lo, rows, cin, cout):
     dw = torch.zeros((cout, cin), dtype=torch.float32, device=dy.device)
     ws_bytes = lib.pv2_wgrad_workspace_bytes(rows, rows, cin, cout)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dy.device)
-    with torch.cuda.device(dy.device):
+    with _lib.on_device(dy.device):
         _lib.check(lib.pv2_dense_wgrad(_lib.C.c_void_p(x.data_ptr()), x_row, x_lo, _lib.C.c_void_p(dy.data_ptr()), dy_row,
                                        dy_lo, rows, cin, cout, _lib.ptr(dw), _lib.ptr(ws), ws_bytes, _lib.stream_ptr()),
                    "pv2_dense_wgrad")
@@ -63,7 +63,7 @@ def coarse_sdf(vol_cl: torch.Tensor, pts: torch.Tensor, M0, c0, wcat4, c14) -> t
     dev = pts.device
     xa = torch.empty((P, 192), dtype=torch.float32, device=dev)  # [a(128) | f_s(64)], plain fp32 (split on chip)
     pts = pts.contiguous()
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         _lib.check(lib.pv2_field_sample_fwd(_lib.ptr(vol_cl), _lib.ptr(pts), P, Z, Y, X, C, 64, 64,
                                             _lib.C.c_void_p(xa.data_ptr() + 128 * 4), 192, 0, None, 0,
                                             _lib.stream_ptr()), "pv2_field_sample_fwd")
@@ -94,7 +94,7 @@ class FusedFieldFunction(torch.autograd.Function):
         grad = torch.empty((P, 3), dtype=torch.float32, device=dev)
         rgb = torch.empty((P, 3), dtype=torch.float32, device=dev)
         sp = _lib.stream_ptr
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             _lib.check(lib.pv2_field_sample_fwd(_lib.ptr(vol_cl), _lib.ptr(pts), P, Z, Y, X, C, 128, 64,
                                                 _lib.C.c_void_p(xa.data_ptr() + 128 * 4), 192, 0, _lib.ptr(f_r), 64,
                                                 sp()), "pv2_field_sample_fwd")
@@ -105,7 +105,7 @@ class FusedFieldFunction(torch.autograd.Function):
         # u = (M0 * W1[0])^T s + M1[0]
         _linear(s_act, 128, 0, False, wp, m10, u, 64, 0, False, 0, None, 0, 0, P, 128, 64)
         Mr_c, cr_c = Mr.contiguous(), cr.contiguous()
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             _lib.check(lib.pv2_field_post_fwd(_lib.ptr(vol_cl), _lib.ptr(pts), _lib.ptr(dirs), samples_per_ray,
                                               _lib.ptr(u), _lib.ptr(f_r), _lib.C.c_void_p(out.data_ptr() + 4), 68,
                                               _lib.ptr(Mr_c), _lib.ptr(cr_c), P, Z, Y, X, C, _lib.ptr(grad),
@@ -131,7 +131,7 @@ class FusedFieldFunction(torch.autograd.Function):
         dMr, dcr = small[:402].view(3, 134), small[402:405]
         d_m10, d_c1 = small[405:469], small[469:537]
         sp = _lib.stream_ptr
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             _lib.check(lib.pv2_field_post_bwd(_lib.ptr(vol_cl), _lib.ptr(pts), _lib.ptr(dirs), ctx.spr, _lib.ptr(f_r),
                                               _lib.C.c_void_p(out.data_ptr() + 4), 68, _lib.ptr(grad), _lib.ptr(rgb),
                                               _lib.ptr(Mr), _lib.ptr(g_rgb), _lib.ptr(g_grad), _lib.ptr(g_sdf), P, Z, Y,
@@ -152,7 +152,7 @@ class FusedFieldFunction(torch.autograd.Function):
         d_M0 = _dense_wgrad(xa[:, 128:], 192, 0, hbar, 128, 0, P, 64, 128)
         d_c0 = hbar.sum(0)
         dvol = torch.zeros_like(vol_cl)
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             _lib.check(lib.pv2_field_sample_bwd(_lib.ptr(pts), _lib.ptr(dF), 128, _lib.ptr(u), _lib.ptr(gbar), P, Z, Y, X,
                                                 C, 64, _lib.ptr(dvol), sp()), "pv2_field_sample_bwd")
         return dvol, None, None, None, d_M0, d_c0, d_wcat, d_c1.clone(), d_wp, d_m10.clone(), dMr.clone(), dcr.clone()

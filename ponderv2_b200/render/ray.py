@@ -35,7 +35,7 @@ def ray_setup(origins: torch.Tensor, directions: torch.Tensor, s0: int, bbox: Se
     pts = torch.empty((R, s0, 3), dtype=torch.float32, device=dev)
     nz = _f32c(noise)
     bb = (_lib.C.c_float * 6)(*[float(b) for b in bbox])
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         _lib.check(lib.pv2_ray_setup(_lib.ptr(o), _lib.ptr(d), _lib.ptr(nz), nz.shape[1] if nz is not None else 0, R, s0,
                                      bb, float(near_plane), _lib.ptr(nears), _lib.ptr(fars), _lib.ptr(bins),
                                      _lib.ptr(pts), _lib.stream_ptr()), "pv2_ray_setup")
@@ -60,7 +60,7 @@ def ray_resample(origins, directions, nears, fars, bins, sdf_coarse, si: int, in
     new_bins = torch.empty((R, si), dtype=torch.float32, device=dev)
     minmax = torch.empty(2, dtype=torch.int32, device=dev)
     nz = _f32c(noise)
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         _lib.check(lib.pv2_ray_resample(_lib.ptr(o), _lib.ptr(d), _lib.ptr(nears), _lib.ptr(fars), _lib.ptr(bins),
                                         _lib.ptr(sdf), _lib.ptr(nz), nz.shape[1] if nz is not None else 0, R, s0, si,
                                         float(inv_s), int(bool(norm_pts)), float(norm_padding), _lib.ptr(starts),
@@ -85,7 +85,7 @@ class RayComposite(torch.autograd.Function):
         depth = torch.empty(R, dtype=torch.float32, device=dev)
         normal = torch.empty((R, 3), dtype=torch.float32, device=dev)
         rgb = torch.empty((R, 3), dtype=torch.float32, device=dev) if rgbs is not None else None
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             _lib.check(lib.pv2_ray_composite_fwd(_lib.ptr(sdf), _lib.ptr(grad), _lib.ptr(rgbs), _lib.ptr(starts),
                                                  _lib.ptr(deltas), _lib.ptr(dirs), _lib.ptr(var), _lib.ptr(minmax),
                                                  float(cos_anneal), R, S, int(bool(clamp_rgb)), _lib.ptr(weights),
@@ -109,7 +109,7 @@ class RayComposite(torch.autograd.Function):
         g_var = torch.zeros(1, dtype=torch.float32, device=dev)
         if not ctx.has_rgb:
             g_rgb = None
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             _lib.check(lib.pv2_ray_composite_bwd(_lib.ptr(sdf), _lib.ptr(grad), _lib.ptr(rgbs_p), _lib.ptr(starts),
                                                  _lib.ptr(deltas), _lib.ptr(dirs), _lib.ptr(var), _lib.ptr(minmax),
                                                  ctx.cos_anneal, R, S, _lib.ptr(_f32c(g_rgb)), _lib.ptr(_f32c(g_depth)),
@@ -133,7 +133,7 @@ class RayLoss(torch.autograd.Function):
         R, S = sdf.shape
         dev = sdf.device
         sums = torch.empty(11, dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             _lib.check(lib.pv2_ray_loss_fwd(_lib.ptr(dp), _lib.ptr(rp), _lib.ptr(dg), _lib.ptr(rg), _lib.ptr(sdf),
                                             _lib.ptr(z), _lib.ptr(grad), R, S, float(trunc), _lib.ptr(sums),
                                             _lib.stream_ptr()), "pv2_ray_loss_fwd")
@@ -158,7 +158,7 @@ class RayLoss(torch.autograd.Function):
         g_rgb = torch.empty((R, 3), dtype=torch.float32, device=dev) if ctx.has_rgb else None
         g_sdf = torch.empty((R, S), dtype=torch.float32, device=dev)
         g_grad = torch.empty((R, S, 3), dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             _lib.check(lib.pv2_ray_loss_bwd(_lib.ptr(dp), _lib.ptr(rp if ctx.has_rgb else None), _lib.ptr(dg),
                                             _lib.ptr(rg if ctx.has_rgb else None), _lib.ptr(sdf), _lib.ptr(z),
                                             _lib.ptr(grad), R, S, ctx.trunc, _lib.ptr(coef), _lib.ptr(g_depth),

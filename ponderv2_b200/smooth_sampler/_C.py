@@ -31,7 +31,7 @@ def forward(input, grid, padding_mode: int, align_corners: bool, apply_smoothste
     N, C, D, H, W, P = _dims(input, grid)
     out = torch.empty((N, C, grid.shape[1], grid.shape[2], grid.shape[3]), dtype=input.dtype, device=input.device)
     lib = _lib.load()
-    with torch.cuda.device(input.device):
+    with _lib.on_device(input.device):
         _lib.check(lib.pv2_trilinear_fwd(_lib.ptr(input), _lib.ptr(grid), _lib.ptr(out), N, C, D, H, W, P,
                                          int(padding_mode), int(align_corners), int(apply_smoothstep),
                                          _lib.dtype_code(input.dtype), _lib.stream_ptr()), "pv2_trilinear_fwd")
@@ -47,7 +47,7 @@ def backward(grad_output, input, grid, padding_mode: int, align_corners: bool, a
     grad_input = torch.zeros_like(input) if input_requires_grad else None
     grad_grid = torch.empty_like(grid)
     lib = _lib.load()
-    with torch.cuda.device(input.device):
+    with _lib.on_device(input.device):
         _lib.check(lib.pv2_trilinear_bwd(_lib.ptr(grad_output), _lib.ptr(input), _lib.ptr(grid), _lib.ptr(grad_input),
                                          _lib.ptr(grad_grid), N, C, D, H, W, P, int(padding_mode), int(align_corners),
                                          int(apply_smoothstep), _lib.dtype_code(input.dtype), _lib.stream_ptr()),
@@ -68,7 +68,7 @@ def backward_backward(grad_out_input, grad_out_grid, input, grid, grad_output, p
     grad_grid = torch.empty_like(grid)
     grad_grad_out = torch.zeros_like(grad_output)
     lib = _lib.load()
-    with torch.cuda.device(input.device):
+    with _lib.on_device(input.device):
         _lib.check(lib.pv2_trilinear_bwd_bwd(_lib.ptr(grad_out_input) if input_requires_grad else None,
                                              _lib.ptr(grad_out_grid), _lib.ptr(input), _lib.ptr(grid),
                                              _lib.ptr(grad_output), _lib.ptr(grad_input), _lib.ptr(grad_grid),

@@ -62,7 +62,7 @@ def build_tile_map(nbr: torch.Tensor) -> TileMap:
     blk = torch.empty((kvol, (n + 31) // 32), dtype=torch.uint8, device=dev)
     ws_bytes = lib.pv2_rulebook_row_order_workspace_bytes(n)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         _lib.check(lib.pv2_rulebook_row_order(_lib.ptr(nbr), n, kvol, _lib.ptr(order), _lib.ptr(nbr_sorted),
                                               _lib.ptr(blk), _lib.ptr(ws), ws_bytes, _lib.stream_ptr()),
                    "pv2_rulebook_row_order")
@@ -125,7 +125,7 @@ def build_subm_rulebook(indices: torch.Tensor, spatial_shape: Sequence[int], ksi
     ws_bytes = lib.pv2_rulebook_workspace_bytes(n)
     ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=indices.device)
     pc = torch.zeros(1, dtype=torch.int64, device=indices.device) if count_pairs else None
-    with torch.cuda.device(indices.device):
+    with _lib.on_device(indices.device):
         _lib.check(lib.pv2_rulebook_subm(_lib.ptr(indices), n, _lib.i32x3(spatial_shape), ksize, _lib.ptr(nbr),
                                          _lib.ptr(pc), _lib.ptr(ws), ws_bytes, _lib.stream_ptr()),
                    "pv2_rulebook_subm")
@@ -144,7 +144,7 @@ def build_down_rulebook(indices: torch.Tensor, spatial_shape: Sequence[int]) -> 
     n_out_dev = torch.zeros(1, dtype=torch.int32, device=dev)
     ws_bytes = lib.pv2_rulebook_workspace_bytes(n)
     ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         _lib.check(lib.pv2_rulebook_down(_lib.ptr(indices), n, _lib.i32x3(spatial_shape), _lib.ptr(out_coords),
                                          _lib.ptr(in2out), _lib.ptr(koff), _lib.ptr(n_out_dev), _lib.ptr(ws),
                                          ws_bytes, _lib.stream_ptr()), "pv2_rulebook_down")
@@ -175,7 +175,7 @@ def _gather_gemm(x: torch.Tensor, w3: torch.Tensor, bias: Optional[torch.Tensor]
     dcode = _lib.dtype_code(x.dtype)
     ws_bytes = lib.pv2_spconv_workspace_bytes(x.shape[0], cin, cout, kvol, dcode)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes else None
-    with torch.cuda.device(x.device), _lib.timed("pv2_spconv_gather_gemm", nbytes, 0):
+    with _lib.on_device(x.device), _lib.timed("pv2_spconv_gather_gemm", nbytes, 0):
         _lib.check(lib.pv2_spconv_gather_gemm(_lib.ptr(x), _lib.C.c_void_p(w3.data_ptr()), w3.stride(0), w3.stride(1),
                                               _lib.ptr(bias), _lib.ptr(nbr), _lib.ptr(order), _lib.ptr(y), x.shape[0],
                                               n_out, cin,
@@ -206,7 +206,7 @@ def _wgrad(x: torch.Tensor, dy: torch.Tensor, tmap: TileMap, kvol: int, out: Opt
     nbytes = x.shape[0] * cin * b + dy.shape[0] * cout * b + kvol * cin * cout * 4 + 4 * kvol * dy.shape[0]
     ws_bytes = lib.pv2_wgrad_workspace_bytes(x.shape[0], dy.shape[0], cin, cout) if x.dtype == torch.float32 else 0
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes else None
-    with torch.cuda.device(x.device), _lib.timed("pv2_spconv_wgrad", nbytes, 0):
+    with _lib.on_device(x.device), _lib.timed("pv2_spconv_wgrad", nbytes, 0):
         _lib.check(lib.pv2_spconv_wgrad(_lib.ptr(x.contiguous()), _lib.ptr(dy.contiguous()), _lib.ptr(nbr),
                                         _lib.ptr(order), _lib.ptr(tmap.blk_active), _lib.ptr(dw), x.shape[0],
                                         dy.shape[0], cin, cout, kvol,
@@ -264,7 +264,7 @@ class _SparseConvFunction(torch.autograd.Function):
             cout_, kvol_, cin_ = w3.shape
             wt = torch.empty((cin_, kvol_, cout_), dtype=w3.dtype, device=w3.device)   # [Cin, K, Cout], k-flipped for SubM
             lib = _lib.load()
-            with torch.cuda.device(w3.device):
+            with _lib.on_device(w3.device):
                 _lib.check(lib.pv2_spconv_dgrad_weights(_lib.ptr(w3.contiguous()), _lib.ptr(wt), cout_, kvol_, cin_,
                                                         int(ctx.flip), _lib.dtype_code(w3.dtype), _lib.stream_ptr()),
                            "pv2_spconv_dgrad_weights")
