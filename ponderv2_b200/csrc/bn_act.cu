@@ -188,6 +188,140 @@ __global__ void bn_apply_bwd_kernel(const void* __restrict__ x, const void* __re
   }
 }
 
+// ---- small batches (N <= kSmallN rows: the deep U-Net levels, 381 / 1567 voxels at C2) ---------------------------------
+// One launch instead of three: a block owns 32 channels (8 float4 groups x 32 row lanes), sums its rows, reduces through
+// shared memory in a fixed order (deterministic, double precision like the two-level path), then applies.  The second pass
+// re-reads rows that are still in L1/L2; three ~7 us launches become one.
+constexpr int kSmallN = 2048;
+
+template <bool kBf16>
+__global__ void __launch_bounds__(256) bn_small_fwd_kernel(const void* __restrict__ x, const void* __restrict__ res,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                           float* __restrict__ running_mean, float* __restrict__ running_var,
+                                                           float momentum, float eps, int relu, int64_t N, int C4,
+                                                           void* __restrict__ y, float* __restrict__ mean,
+                                                           float* __restrict__ invstd) {
+  __shared__ double s_a[32][8][4], s_b[32][8][4];
+  __shared__ float s_mu[8][4], s_is[8][4];
+  const int cgl = threadIdx.x & 7, rl = threadIdx.x >> 3;
+  const int cg = blockIdx.x * 8 + cgl;
+  const bool on = cg < C4;
+  double a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
+  if (on) {
+    for (int64_t r = rl; r < N; r += 32) {
+      const float4 v = ld4<kBf16>(x, r * C4 + cg);
+      a[0] += v.x; a[1] += v.y; a[2] += v.z; a[3] += v.w;
+      b[0] += (double)v.x * v.x; b[1] += (double)v.y * v.y; b[2] += (double)v.z * v.z; b[3] += (double)v.w * v.w;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { s_a[rl][cgl][i] = a[i]; s_b[rl][cgl][i] = b[i]; }
+  __syncthreads();
+  if (rl == 0 && on) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      double sa = 0.0, sb = 0.0;
+      for (int r = 0; r < 32; ++r) { sa += s_a[r][cgl][i]; sb += s_b[r][cgl][i]; }
+      const double m = sa / (double)N;
+      double var = sb / (double)N - m * m;
+      if (var < 0.0) var = 0.0;
+      const int c = cg * 4 + i;
+      const float is = (float)(1.0 / sqrt(var + (double)eps));
+      s_mu[cgl][i] = (float)m; s_is[cgl][i] = is;
+      mean[c] = (float)m; invstd[c] = is;
+      if (running_mean != nullptr) {
+        const double unb = N > 1 ? var * (double)N / (double)(N - 1) : var;
+        running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * m);
+        running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unb);
+      }
+    }
+  }
+  __syncthreads();
+  if (!on) return;
+  const float4 mu = make_float4(s_mu[cgl][0], s_mu[cgl][1], s_mu[cgl][2], s_mu[cgl][3]);
+  const float4 is = make_float4(s_is[cgl][0], s_is[cgl][1], s_is[cgl][2], s_is[cgl][3]);
+  const float4 ga = *reinterpret_cast<const float4*>(gamma + cg * 4);
+  const float4 be = *reinterpret_cast<const float4*>(beta + cg * 4);
+  for (int64_t r = rl; r < N; r += 32) {
+    const int64_t e = r * C4 + cg;
+    const float4 v = ld4<kBf16>(x, e);
+    float4 o;
+    o.x = (v.x - mu.x) * is.x * ga.x + be.x; o.y = (v.y - mu.y) * is.y * ga.y + be.y;
+    o.z = (v.z - mu.z) * is.z * ga.z + be.z; o.w = (v.w - mu.w) * is.w * ga.w + be.w;
+    if (res != nullptr) { const float4 q = ld4<kBf16>(res, e); o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w; }
+    if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+    st4<kBf16>(y, e, o);
+  }
+}
+
+template <bool kBf16>
+__global__ void __launch_bounds__(256) bn_small_bwd_kernel(const void* __restrict__ x, const void* __restrict__ dy,
+                                                           const void* __restrict__ y, const float* __restrict__ mean,
+                                                           const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                                           int relu, int64_t N, int C4, void* __restrict__ dx,
+                                                           void* __restrict__ dres, float* __restrict__ dgamma,
+                                                           float* __restrict__ dbeta) {
+  __shared__ double s_a[32][8][4], s_b[32][8][4];
+  __shared__ float s_dg[8][4], s_db[8][4];
+  const int cgl = threadIdx.x & 7, rl = threadIdx.x >> 3;
+  const int cg = blockIdx.x * 8 + cgl;
+  const bool on = cg < C4;
+  float4 mu = make_float4(0.f, 0.f, 0.f, 0.f), is = mu, ga = mu;
+  if (on) {
+    mu = *reinterpret_cast<const float4*>(mean + cg * 4);
+    is = *reinterpret_cast<const float4*>(invstd + cg * 4);
+    ga = *reinterpret_cast<const float4*>(gamma + cg * 4);
+  }
+  auto dz_of = [&](int64_t e) {
+    float4 g = ld4<kBf16>(dy, e);
+    if (relu) {
+      const float4 o = ld4<kBf16>(y, e);
+      g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f; g.z = o.z > 0.f ? g.z : 0.f; g.w = o.w > 0.f ? g.w : 0.f;
+    }
+    return g;
+  };
+  double a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
+  if (on) {
+    for (int64_t r = rl; r < N; r += 32) {
+      const int64_t e = r * C4 + cg;
+      const float4 v = ld4<kBf16>(x, e);
+      const float4 g = dz_of(e);
+      a[0] += g.x; a[1] += g.y; a[2] += g.z; a[3] += g.w;
+      b[0] += (double)g.x * ((v.x - mu.x) * is.x); b[1] += (double)g.y * ((v.y - mu.y) * is.y);
+      b[2] += (double)g.z * ((v.z - mu.z) * is.z); b[3] += (double)g.w * ((v.w - mu.w) * is.w);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { s_a[rl][cgl][i] = a[i]; s_b[rl][cgl][i] = b[i]; }
+  __syncthreads();
+  if (rl == 0 && on) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      double sa = 0.0, sb = 0.0;
+      for (int r = 0; r < 32; ++r) { sa += s_a[r][cgl][i]; sb += s_b[r][cgl][i]; }
+      s_db[cgl][i] = (float)sa; s_dg[cgl][i] = (float)sb;
+      dbeta[cg * 4 + i] = (float)sa; dgamma[cg * 4 + i] = (float)sb;
+    }
+  }
+  __syncthreads();
+  if (!on) return;
+  const float inv_n = 1.0f / (float)N;
+  const float4 dg = make_float4(s_dg[cgl][0], s_dg[cgl][1], s_dg[cgl][2], s_dg[cgl][3]);
+  const float4 db = make_float4(s_db[cgl][0], s_db[cgl][1], s_db[cgl][2], s_db[cgl][3]);
+  for (int64_t r = rl; r < N; r += 32) {
+    const int64_t e = r * C4 + cg;
+    const float4 v = ld4<kBf16>(x, e);
+    const float4 g = dz_of(e);
+    if (dres != nullptr) st4<kBf16>(dres, e, g);
+    float4 d;
+    d.x = ga.x * is.x * (g.x - db.x * inv_n - (v.x - mu.x) * is.x * dg.x * inv_n);
+    d.y = ga.y * is.y * (g.y - db.y * inv_n - (v.y - mu.y) * is.y * dg.y * inv_n);
+    d.z = ga.z * is.z * (g.z - db.z * inv_n - (v.z - mu.z) * is.z * dg.z * inv_n);
+    d.w = ga.w * is.w * (g.w - db.w * inv_n - (v.w - mu.w) * is.w * dg.w * inv_n);
+    st4<kBf16>(dx, e, d);
+  }
+}
+
 inline int nblocks_for(int64_t n) { return (int)((n + kRowsPerBlock - 1) / kRowsPerBlock); }
 inline bool shape_ok(int64_t n, int c) { return n >= 0 && c >= 4 && c <= 1024 && (c % 4) == 0 && (kBnThreads / (c / 4)) >= 1; }
 
@@ -214,6 +348,11 @@ static int bn_fwd_t(const void* x, const void* res, const float* gamma, const fl
   PV2_CHECK_ARG((((uintptr_t)mean | (uintptr_t)invstd | (uintptr_t)gamma | (uintptr_t)beta) & 15) == 0);
   if (workspace_bytes < pv2_bn_workspace_bytes(n, c)) return PV2_EWORKSPACE;
   const int nblk = nblocks_for(n), C4 = c / 4;
+  if (n <= kSmallN) {
+    bn_small_fwd_kernel<kBf16><<<(C4 + 7) / 8, 256, 0, stream>>>(x, res, gamma, beta, running_mean, running_var, momentum, eps,
+                                                                relu, n, C4, y, mean, invstd);
+    PV2_DONE(1);
+  }
   bn_partial_kernel<0, kBf16><<<nblk, kBnThreads, 0, stream>>>(x, nullptr, nullptr, nullptr, nullptr, n, C4, 0,
                                                                 (float4*)workspace);
   bn_finalize_kernel<0><<<(c + 31) / 32, 1024, 0, stream>>>((const float*)workspace, nblk, c, n, eps, momentum, mean, invstd,
@@ -236,6 +375,11 @@ static int bn_bwd_t(const void* x, const void* dy, const void* y, const float* g
   PV2_CHECK_ARG((((uintptr_t)mean | (uintptr_t)invstd | (uintptr_t)gamma | (uintptr_t)dgamma | (uintptr_t)dbeta) & 15) == 0);
   if (workspace_bytes < pv2_bn_workspace_bytes(n, c)) return PV2_EWORKSPACE;
   const int nblk = nblocks_for(n), C4 = c / 4;
+  if (n <= kSmallN) {
+    bn_small_bwd_kernel<kBf16><<<(C4 + 7) / 8, 256, 0, stream>>>(x, dy, y, mean, invstd, gamma, relu, n, C4, dx, dres, dgamma,
+                                                                dbeta);
+    PV2_DONE(1);
+  }
   bn_partial_kernel<1, kBf16><<<nblk, kBnThreads, 0, stream>>>(x, dy, y, mean, invstd, n, C4, relu, (float4*)workspace);
   bn_finalize_kernel<1><<<(c + 31) / 32, 1024, 0, stream>>>((const float*)workspace, nblk, c, n, 0.f, 0.f, dgamma, dbeta, nullptr,
                                                              nullptr);

@@ -20,13 +20,14 @@ int pv2_spconv_gather_gemm_umma(const void*, const void*, int64_t, int64_t, cons
 // ---- runtime options (development / A-B switches).  Defaults come from the environment once; tests and benchmarks set
 // them through pv2_set_option.  Names: "gg_tma" (bf16 gather through TMA gather4: -1 auto by size, 0 off, 1 on),
 // "gg_bx3" (fp32 gather-GEMM as bf16x3: 0 / 1), "wgrad_mn" (MN-major bf16 weight-gradient kernel: 0 / 1).
-static int g_opt_gg_tma = -2, g_opt_gg_bx3 = -2, g_opt_wgrad_mn = -2, g_opt_ksplit_max = -2;
+static int g_opt_gg_tma = -2, g_opt_gg_bx3 = -2, g_opt_wgrad_mn = -2, g_opt_ksplit_max = -2, g_opt_linear_bx3 = -2;
 static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
 int pv2_get_option(const char* name) {
   if (name == nullptr) return -1;
   if (!strcmp(name, "gg_tma")) { if (g_opt_gg_tma == -2) g_opt_gg_tma = env_int("PV2_GG_TMA", -1); return g_opt_gg_tma; }
   if (!strcmp(name, "gg_bx3")) { if (g_opt_gg_bx3 == -2) g_opt_gg_bx3 = env_int("PV2_GG_BX3", 1); return g_opt_gg_bx3; }
   if (!strcmp(name, "wgrad_mn")) { if (g_opt_wgrad_mn == -2) g_opt_wgrad_mn = env_int("PV2_WGRAD_MN", 1); return g_opt_wgrad_mn; }
+  if (!strcmp(name, "linear_bx3")) { if (g_opt_linear_bx3 == -2) g_opt_linear_bx3 = env_int("PV2_LINEAR_BX3", 1); return g_opt_linear_bx3; }
   if (!strcmp(name, "gg_ksplit_max")) { if (g_opt_ksplit_max == -2) g_opt_ksplit_max = env_int("PV2_GG_KSPLIT_MAX", 0); return g_opt_ksplit_max; }
   return -1;
 }
@@ -36,6 +37,7 @@ int pv2_set_option(const char* name, int value) {
   if (!strcmp(name, "gg_bx3")) { g_opt_gg_bx3 = value; return 0; }
   if (!strcmp(name, "wgrad_mn")) { g_opt_wgrad_mn = value; return 0; }
   if (!strcmp(name, "gg_ksplit_max")) { g_opt_ksplit_max = value; return 0; }
+  if (!strcmp(name, "linear_bx3")) { g_opt_linear_bx3 = value; return 0; }
   return PV2_EINVAL;
 }
 

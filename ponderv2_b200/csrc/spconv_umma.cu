@@ -1345,6 +1345,9 @@ int launch(const GGParams& p0, cudaStream_t stream) {
   if (kSplit && !p.y_split && p.act == 0 && tiles * 2 <= PV2_SM_COUNT && p.num_chunks >= 16) {  // (act: one writer per row)
     ksplit = (PV2_SM_COUNT + (int)tiles - 1) / (int)tiles;  // ~one CTA per SM in total
     if (ksplit > p.num_chunks / 8) ksplit = p.num_chunks / 8;
+    // measured (profiles/r2g_ksplit.txt): with >= 8 row tiles 8 slices beat 12 (L3: 55 vs 61 us; fewer partial tiles to
+    // reduce through global atomics), with 3 tiles (L4) more slices win (31 vs 55 us)
+    if (tiles >= 8 && ksplit > 8) ksplit = 8;
     const int cap = pv2_get_option("gg_ksplit_max");
     if (cap > 0 && ksplit > cap) ksplit = cap;
     if (ksplit < 1) ksplit = 1;
@@ -1469,16 +1472,18 @@ int pv2_spconv_gather_gemm_umma(const void* x, const void* w, int64_t w_sco, int
 //   y[j, 0:cout] = act( x[j, 0:cin] . w[0:cout, 0:cin]^T + bias )          fp32 storage, 3xTF32 arithmetic
 // x is plain fp32 (x_presplit = 0) or split-precision (hi at x[j*x_row + c], lo at +x_lo_off; the halves are summed on
 // load).  y / y2 can be written plain or split.
+// room for the weights pre-split into bf16 hi / lo halves (bf16x3 arithmetic, weights by TMA); 0 for shapes that stay 3xTF32
 size_t pv2_linear_workspace_bytes(int64_t rows, int cin, int cout, int x_presplit) {
-  (void)rows; (void)cin; (void)cout; (void)x_presplit;
-  return 0;
+  (void)rows;
+  if (x_presplit || cin <= 0 || cout <= 0 || (cin % 8) != 0) return 0;
+  const size_t r = ((size_t)cout + 15) / 16 * 16, c = ((size_t)cin + 63) / 64 * 64;
+  return (2 * r * c * 2 + 255) / 256 * 256;
 }
 
 int pv2_linear(const float* x, int64_t x_row, int64_t x_lo_off, int x_presplit, const float* w, const float* bias,
                float* y, int64_t y_row, int64_t y_lo_off, int y_split, int act, float* y2, int64_t y2_row,
                int64_t y2_lo_off, int64_t rows, int cin, int cout, void* workspace, size_t workspace_bytes,
                void* stream_) {
-  (void)workspace; (void)workspace_bytes;
   PV2_CHECK_ARG(rows >= 0 && cin > 0 && cout > 0 && cout <= 256 && (cin % 4) == 0 && act >= 0 && act <= 4);
   PV2_CHECK_ARG((act != 2 && act != 3) || y2 != nullptr);
   PV2_CHECK_ARG(act < 2 || !y_split);
@@ -1495,6 +1500,21 @@ int pv2_linear(const float* x, int64_t x_row, int64_t x_lo_off, int x_presplit, 
   p.y2 = y2; p.y2_row = y2_row; p.y2_lo_off = y2_lo_off;
   if (x_presplit) return launch<true, true, 2>(p, (cudaStream_t)stream_);
   {
+    // bf16x3 persistent kernel (same arithmetic as the sparse convolutions) when the rows fill the SMs and the caller
+    // brought the weight workspace; "linear_bx3" = 0 keeps the 3xTF32 kernel (A/B switch)
+    const size_t need = pv2_linear_workspace_bytes(rows, cin, cout, 0);
+    if (pv2_get_option("linear_bx3") != 0 && need > 0 && workspace != nullptr && workspace_bytes >= need &&
+        ((uintptr_t)workspace & 127) == 0 && rows >= 128 * PV2_SM_COUNT && tensor_map_encoder() != nullptr) {
+      cudaStream_t stream = (cudaStream_t)stream_;
+      const int w2_rows = (cout + 15) / 16 * 16, w2_cols = (cin + 63) / 64 * 64;
+      presplit_weights_bf16_kernel<<<pv2_grid_for((int64_t)w2_rows * w2_cols, 256), 256, 0, stream>>>(
+          w, cin, cin, cout, 1, cin, (__nv_bfloat16*)workspace, w2_rows, w2_cols);
+      pv2_note_launches(1);
+      GGParams q = p;
+      q.w2_row0 = 0; q.w2_rows = w2_rows;
+      const int rb = launch_persistent(q, stream, workspace, w2_cols);
+      if (rb != PV2_EUNSUPPORTED) return rb;
+    }
     const int rp = launch_persistent(p, (cudaStream_t)stream_);
     if (rp != PV2_EUNSUPPORTED) return rp;
   }

@@ -15,6 +15,8 @@ for path in sys.argv[1:]:
     if len(rows) < 2:
         print(path, "empty"); continue
     h = rows[0]
+    if "Metric Name" not in h:
+        print(path, "no metric table:", " ".join(rows[0])[:120]); continue
     iname, ival, iunit, ik = h.index("Metric Name"), h.index("Metric Value"), h.index("Metric Unit"), h.index("Kernel Name")
     print(f"== {path}: {rows[1][ik][:90]}")
     seen = set()
