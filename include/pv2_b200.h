@@ -152,9 +152,10 @@ int pv2_bn_act_bwd(const float* x, const float* dy, const float* y, const float*
 int pv2_bn_act_fwd_t(const void* x, const void* res, const float* gamma, const float* beta, float* running_mean,
                      float* running_var, float momentum, float eps, int relu, int64_t n, int c, void* y, float* mean,
                      float* invstd, int dtype, void* workspace, size_t workspace_bytes, void* stream);
+/* accumulate != 0: dgamma / dbeta are ADDED to (slices of the caller's flat gradient buffer) instead of overwritten */
 int pv2_bn_act_bwd_t(const void* x, const void* dy, const void* y, const float* gamma, const float* mean,
                      const float* invstd, int relu, int64_t n, int c, void* dx, void* dres, float* dgamma, float* dbeta,
-                     int dtype, void* workspace, size_t workspace_bytes, void* stream);
+                     int accumulate, int dtype, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Densify: voxel features -> dense channels-last volume, scatter-mean

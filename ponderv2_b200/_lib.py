@@ -63,7 +63,7 @@ SIGNATURES = {
     "pv2_bn_act_bwd": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _i64, _int, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pv2_bn_act_fwd_t": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_float, C.c_float, _int, _i64, _int, _vp, _vp, _vp, _int, _vp, _sz,
                                  _vp]),
-    "pv2_bn_act_bwd_t": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _i64, _int, _vp, _vp, _vp, _vp, _int, _vp, _sz, _vp]),
+    "pv2_bn_act_bwd_t": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _i64, _int, _vp, _vp, _vp, _vp, _int, _int, _vp, _sz, _vp]),
     "pv2_densify_fwd": (_int, [_vp, _vp, _i64, _int, _i64, _vp, _vp, _vp]),
     "pv2_densify_bwd": (_int, [_vp, _vp, _vp, _i64, _int, _i64, _vp, _vp]),
     "pv2_trilinear_fwd": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _int, _int, _int, _int, _vp]),

@@ -38,6 +38,12 @@ class _BNActFunction(torch.autograd.Function):
                                             _lib.stream_ptr()), "pv2_bn_act_fwd_t")
         ctx.save_for_backward(x, y, gamma, stats)
         ctx.relu, ctx.has_res = bool(relu), res is not None
+        # parameters re-homed by dist.FlatParameters: dgamma / dbeta are accumulated by the kernel straight into their
+        # slices of the flat gradient buffer (no temporaries, no autograd accumulation kernels)
+        sg, sb = getattr(gamma, "_pv2_sink", None), getattr(beta, "_pv2_sink", None)
+        ok = (sg is not None and sb is not None and sg[0] is sb[0] and sg[1].dtype == torch.float32
+              and sb[1].dtype == torch.float32 and sg[1].is_contiguous() and sb[1].is_contiguous())
+        ctx.sinks = (sg, sb, gamma, beta) if ok else None
         return y
 
     @staticmethod
@@ -49,15 +55,23 @@ class _BNActFunction(torch.autograd.Function):
         dy = dy.contiguous().to(x.dtype)
         dx = torch.empty_like(x)
         dres = torch.empty_like(x) if ctx.has_res else None
-        dgb = torch.empty((2, c), dtype=torch.float32, device=dev)
+        if ctx.sinks is not None:
+            (flat, g_view), (_, b_view), p_gamma, p_beta = ctx.sinks
+            dg_t, db_t, acc = g_view, b_view, 1
+        else:
+            dgb = torch.empty((2, c), dtype=torch.float32, device=dev)
+            dg_t, db_t, acc = dgb[0], dgb[1], 0
         ws_bytes = lib.pv2_bn_workspace_bytes(n, c)
         ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
         with _lib.on_device(dev):
             _lib.check(lib.pv2_bn_act_bwd_t(_lib.ptr(x), _lib.ptr(dy), _lib.ptr(y), _lib.ptr(gamma.contiguous()),
                                             _lib.ptr(stats[0]), _lib.ptr(stats[1]), int(ctx.relu), n, c, _lib.ptr(dx),
-                                            _lib.ptr(dres), _lib.ptr(dgb[0]), _lib.ptr(dgb[1]), _lib.dtype_code(x.dtype),
+                                            _lib.ptr(dres), _lib.ptr(dg_t), _lib.ptr(db_t), acc, _lib.dtype_code(x.dtype),
                                             _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), "pv2_bn_act_bwd_t")
-        return dx, dres, dgb[0], dgb[1], None, None, None, None, None
+        if acc:
+            flat.mark_ready(p_gamma); flat.mark_ready(p_beta)
+            return dx, dres, None, None, None, None, None, None, None
+        return dx, dres, dg_t, db_t, None, None, None, None, None
 
 
 _NOTED = set()

@@ -102,7 +102,8 @@ template <int MODE>
 __global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restrict__ partial, int nblk, int C, int64_t N,
                                                           float eps, float momentum, float* __restrict__ out_a,
                                                           float* __restrict__ out_b, float* __restrict__ running_mean,
-                                                          float* __restrict__ running_var) {
+                                                          float* __restrict__ running_var, float* __restrict__ acc_a,
+                                                          float* __restrict__ acc_b) {
   __shared__ double s_a[32][32], s_b[32][32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;
@@ -132,8 +133,9 @@ __global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restri
       running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unb);
     }
   } else {
-    out_a[c] = (float)sb;   // dgamma
+    out_a[c] = (float)sb;   // dgamma of this call (bn_apply_bwd reads it)
     out_b[c] = (float)sa;   // dbeta
+    if (acc_a != nullptr) { acc_a[c] += (float)sb; acc_b[c] += (float)sa; }   // ... and accumulated into the caller's buffer
   }
 }
 
@@ -260,7 +262,7 @@ __global__ void __launch_bounds__(256) bn_small_bwd_kernel(const void* __restric
                                                            const float* __restrict__ invstd, const float* __restrict__ gamma,
                                                            int relu, int64_t N, int C4, void* __restrict__ dx,
                                                            void* __restrict__ dres, float* __restrict__ dgamma,
-                                                           float* __restrict__ dbeta) {
+                                                           float* __restrict__ dbeta, int accumulate) {
   __shared__ double s_a[32][8][4], s_b[32][8][4];
   __shared__ float s_dg[8][4], s_db[8][4];
   const int cgl = threadIdx.x & 7, rl = threadIdx.x >> 3;
@@ -300,7 +302,8 @@ __global__ void __launch_bounds__(256) bn_small_bwd_kernel(const void* __restric
       double sa = 0.0, sb = 0.0;
       for (int r = 0; r < 32; ++r) { sa += s_a[r][cgl][i]; sb += s_b[r][cgl][i]; }
       s_db[cgl][i] = (float)sa; s_dg[cgl][i] = (float)sb;
-      dbeta[cg * 4 + i] = (float)sa; dgamma[cg * 4 + i] = (float)sb;
+      if (accumulate) { dbeta[cg * 4 + i] += (float)sa; dgamma[cg * 4 + i] += (float)sb; }
+      else { dbeta[cg * 4 + i] = (float)sa; dgamma[cg * 4 + i] = (float)sb; }
     }
   }
   __syncthreads();
@@ -331,7 +334,7 @@ extern "C" {
 
 size_t pv2_bn_workspace_bytes(int64_t n, int c) {
   if (!shape_ok(n, c)) return 0;
-  return ((size_t)nblocks_for(n) * 2 * c * sizeof(float) + 255) / 256 * 256;
+  return (((size_t)nblocks_for(n) * 2 * c + 2 * (size_t)c) * sizeof(float) + 255) / 256 * 256;   // partial sums + one [2][c] scratch
 }
 
 }  // extern "C"
@@ -356,7 +359,7 @@ static int bn_fwd_t(const void* x, const void* res, const float* gamma, const fl
   bn_partial_kernel<0, kBf16><<<nblk, kBnThreads, 0, stream>>>(x, nullptr, nullptr, nullptr, nullptr, n, C4, 0,
                                                                 (float4*)workspace);
   bn_finalize_kernel<0><<<(c + 31) / 32, 1024, 0, stream>>>((const float*)workspace, nblk, c, n, eps, momentum, mean, invstd,
-                                                             running_mean, running_var);
+                                                             running_mean, running_var, nullptr, nullptr);
   const int64_t total4 = n * C4;
   bn_apply_fwd_kernel<kBf16><<<pv2_grid_for(total4, 256), 256, 0, stream>>>(x, res, mean, invstd, gamma, beta, total4, C4,
                                                                            relu, y);
@@ -366,7 +369,7 @@ static int bn_fwd_t(const void* x, const void* res, const float* gamma, const fl
 template <bool kBf16>
 static int bn_bwd_t(const void* x, const void* dy, const void* y, const float* gamma, const float* mean,
                     const float* invstd, int relu, int64_t n, int c, void* dx, void* dres, float* dgamma, float* dbeta,
-                    void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+                    void* workspace, size_t workspace_bytes, cudaStream_t stream, int accumulate = 0) {
   PV2_CHECK_ARG(shape_ok(n, c));
   if (n == 0) return 0;
   PV2_CHECK_ARG(x && dy && gamma && mean && invstd && dx && dgamma && dbeta && workspace && (!relu || y));
@@ -377,14 +380,18 @@ static int bn_bwd_t(const void* x, const void* dy, const void* y, const float* g
   const int nblk = nblocks_for(n), C4 = c / 4;
   if (n <= kSmallN) {
     bn_small_bwd_kernel<kBf16><<<(C4 + 7) / 8, 256, 0, stream>>>(x, dy, y, mean, invstd, gamma, relu, n, C4, dx, dres, dgamma,
-                                                                dbeta);
+                                                                dbeta, accumulate);
     PV2_DONE(1);
   }
   bn_partial_kernel<1, kBf16><<<nblk, kBnThreads, 0, stream>>>(x, dy, y, mean, invstd, n, C4, relu, (float4*)workspace);
-  bn_finalize_kernel<1><<<(c + 31) / 32, 1024, 0, stream>>>((const float*)workspace, nblk, c, n, 0.f, 0.f, dgamma, dbeta, nullptr,
-                                                             nullptr);
+  // accumulate mode: this call's sums go to the scratch behind the partials (read by the apply pass) and are added into
+  // dgamma / dbeta, which then are slices of the caller's gradient buffer
+  float* own_g = accumulate ? (float*)workspace + (size_t)nblk * 2 * c : dgamma;
+  float* own_b = accumulate ? own_g + c : dbeta;
+  bn_finalize_kernel<1><<<(c + 31) / 32, 1024, 0, stream>>>((const float*)workspace, nblk, c, n, 0.f, 0.f, own_g, own_b, nullptr,
+                                                             nullptr, accumulate ? dgamma : nullptr, accumulate ? dbeta : nullptr);
   const int64_t total4 = n * C4;
-  bn_apply_bwd_kernel<kBf16><<<pv2_grid_for(total4, 256), 256, 0, stream>>>(x, dy, y, mean, invstd, gamma, dgamma, dbeta,
+  bn_apply_bwd_kernel<kBf16><<<pv2_grid_for(total4, 256), 256, 0, stream>>>(x, dy, y, mean, invstd, gamma, own_g, own_b,
                                                                            total4, C4, relu, 1.0f / (float)n, dx, dres);
   PV2_DONE(3);
 }
@@ -422,13 +429,13 @@ int pv2_bn_act_fwd_t(const void* x, const void* res, const float* gamma, const f
 
 int pv2_bn_act_bwd_t(const void* x, const void* dy, const void* y, const float* gamma, const float* mean,
                      const float* invstd, int relu, int64_t n, int c, void* dx, void* dres, float* dgamma, float* dbeta,
-                     int dtype, void* workspace, size_t workspace_bytes, void* stream_) {
+                     int accumulate, int dtype, void* workspace, size_t workspace_bytes, void* stream_) {
   if (dtype == PV2_F32)
     return bn_bwd_t<false>(x, dy, y, gamma, mean, invstd, relu, n, c, dx, dres, dgamma, dbeta, workspace, workspace_bytes,
-                           (cudaStream_t)stream_);
+                           (cudaStream_t)stream_, accumulate);
   if (dtype == PV2_BF16)
     return bn_bwd_t<true>(x, dy, y, gamma, mean, invstd, relu, n, c, dx, dres, dgamma, dbeta, workspace, workspace_bytes,
-                          (cudaStream_t)stream_);
+                          (cudaStream_t)stream_, accumulate);
   return PV2_EUNSUPPORTED;
 }
 

@@ -90,6 +90,7 @@ class FlatParameters:
         self._comm_stream = None
         self._works = []
         self._launched = [False] * len(self.chunks)
+        self._next = 0          # next slice to hand to the collective (slices go out in buffer order on every rank)
         self._aux_streams = []  # side streams that write gradients straight into the buffer
         self._frozen = None     # (indices, saved values) of parameters that never get a gradient
         self._steps = 0
@@ -103,6 +104,7 @@ class FlatParameters:
         self._pending = [b - a for (_, _, a, b) in self.chunks]
         self._launched = [False] * len(self.chunks)
         self._works = []
+        self._next = 0
 
     def sync_grads(self) -> None:
         """Make `flat_grad` hold every gradient and every `p.grad` a view of it again (after `model.zero_grad()`,
@@ -214,8 +216,11 @@ class FlatParameters:
         if c is None or not self._overlap:
             return
         self._pending[c] -= 1
-        if self._pending[c] == 0 and not self._launched[c] and _is_dist(self._group):
-            self._launch_chunk(c, self._group)
+        # collectives must be issued in the same order on every rank: slices go out strictly in buffer order
+        while self._next < len(self.chunks) and self._pending[self._next] <= 0 and _is_dist(self._group):
+            if not self._launched[self._next]:
+                self._launch_chunk(self._next, self._group)
+            self._next += 1
 
     def _launch_chunk(self, c: int, group=None) -> None:
         s, e, a, b = self.chunks[c]
