@@ -671,7 +671,8 @@ def test_linear_matches_torch(cuda_lib, rows, cin, cout, act):
         want = v
     elif act == 1:
         want = torch.nn.functional.softplus(v, beta=100)
-        assert (y2.double() - torch.sigmoid(100 * v)).abs().max().item() < 2e-4   # sigmoid(100 h): steep
+        # sigmoid(100 h) has slope 25 at h = 0: the bf16x3 products leave |dh| <= 4e-5 at |h| ~ 3 (3xTF32: 8e-6)
+        assert (y2.double() - torch.sigmoid(100 * v)).abs().max().item() < 1e-3
     elif act == 2:
         want = v * 100 * aux.double() * (1 - aux.double())
     elif act == 3:
