@@ -158,6 +158,23 @@ int pv2_bn_act_bwd_t(const void* x, const void* dy, const void* y, const float* 
                      int accumulate, int dtype, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * SDF decoder of the outdoor configuration (hidden 16, feature width 32, L <= 8 linears, softplus beta = 100):
+ * `SDFDecoder.forward` (render_utils/decoders.py:6-36) fused with the two vector-Jacobian products u = d sdf / d f
+ * [P,32] and v = d sdf / d p [P,3] (direct fc_p path) that `autograd.grad(sdf, points, create_graph=True)`
+ * (fields/sdf_field.py:226-238) needs; u / v may be NULL (no-grad coarse pass).  params: packed
+ * [Wp 16x3 | bp 16 | Fc_l 16x32 (x L) | bc_l 16 (x L) | W_l 16x16 (x L-1), W_last O x 16 | b_l 16 (x L-1), b_last O]
+ * (pv2_sdf_mlp_param_count floats).  bwd: given dL/dsdf, dL/du, dL/dv (any may be NULL) writes fbar = dL/df [P,32] and the
+ * per-layer adjoint vectors A, C [L-1][P][16], Z, D [L][P][16] whose contractions over P are the parameter gradients
+ * (host: ponderv2_b200/render/mlp.py).  F != 32 or H != 16 -> PV2_EUNSUPPORTED.
+ * ------------------------------------------------------------------------------------------ */
+int64_t pv2_sdf_mlp_param_count(int L, int O);
+int pv2_sdf_mlp_fwd(const float* f, const float* pts, const float* params, int L, int F, int H, int O, float points_factor,
+                    int64_t P, float* sdf, float* u, float* v, void* stream);
+int pv2_sdf_mlp_bwd(const float* f, const float* pts, const float* params, int L, int F, int H, int O, float points_factor,
+                    int64_t P, const float* g_sdf, const float* g_u, const float* g_v, float* fbar, float* A, float* C,
+                    float* Z, float* D, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Densify: voxel features -> dense channels-last volume, scatter-mean
  * (ponder_indoor_base.py:177-216,332-342; ponder_outdoor_base.py:178-210).
  * cell: [n] int64 flattened cell id in the OUTPUT memory order, or -1 to drop the row.

@@ -49,6 +49,10 @@ SIGNATURES = {
     "pv2_field_post_bwd": (_int, [_vp, _vp, _vp, _int, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _int,
                                    _int, _int, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pv2_field_sample_bwd": (_int, [_vp, _vp, _i64, _vp, _vp, _i64, _int, _int, _int, _int, _int, _vp, _vp]),
+    "pv2_sdf_mlp_param_count": (_i64, [_int, _int]),
+    "pv2_sdf_mlp_fwd": (_int, [_vp, _vp, _vp, _int, _int, _int, _int, C.c_float, _i64, _vp, _vp, _vp, _vp]),
+    "pv2_sdf_mlp_bwd": (_int, [_vp, _vp, _vp, _int, _int, _int, _int, C.c_float, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                _vp, _vp]),
     "pv2_ray_setup": (_int, [_vp, _vp, _vp, _int, _i64, _int, C.POINTER(C.c_float), C.c_float, _vp, _vp, _vp, _vp, _vp]),
     "pv2_ray_resample": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _i64, _int, _int, C.c_float, _int, C.c_float,
                                  _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -22,7 +22,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from ..smooth_sampler import SmoothSampler
-from . import fused, ray
+from . import fused, mlp, ray
 
 
 _NOTED = set()
@@ -146,6 +146,8 @@ class SDFField(nn.Module):
         self.deviation_network = SingleVarianceNetwork(init_val=beta_init)
         self._cos_anneal_ratio = 1.0
         self.norm_pts, self.norm_padding = norm_pts, norm_padding
+        # fused SDF-decoder kernels for the outdoor decoder shape (render/mlp.py); NeuSModel.use_fused switches it
+        self.use_mlp_kernel = False
 
     def set_cos_anneal_ratio(self, anneal):
         self._cos_anneal_ratio = anneal
@@ -165,6 +167,27 @@ class SDFField(nn.Module):
         h = self.sdf_decoder(points, pf if self.share_volume else torch.chunk(pf, 2, dim=-1)[0])
         return h[..., :1], h[..., 1:], pf
 
+    def mlp_kernel_ok(self, volume_feature) -> bool:
+        return (self.use_mlp_kernel and self.share_volume and len(volume_feature) == 1
+                and volume_feature[0].shape[0] == mlp.F and mlp.eligible(self))
+
+    def sdf_no_grad(self, points, volume_feature):
+        """SDF only, no graph (NeuSSampler's coarse pass): sampler + fused decoder kernel when the shape allows."""
+        if not self.mlp_kernel_ok(volume_feature):
+            return self.get_sdf(points, volume_feature)[0].squeeze(-1)
+        pf = self.feature_sampling(points, volume_feature)
+        packed, L, O, pfac = mlp.pack(self.sdf_decoder)
+        return mlp.sdf_only(pf.reshape(-1, mlp.F), points.reshape(-1, 3), packed, L, O, pfac).view(points.shape[:-1])
+
+    def _forward_mlp_kernel(self, points, volume_feature):
+        """sdf and d sdf / d points with the fused decoder: sdf, u = d sdf/d f, v = d sdf/d p from one kernel, the sampler's
+        own (twice differentiable) backward supplies (d f / d points)^T u."""
+        pf = self.feature_sampling(points, volume_feature)                    # [R,S,32], differentiable in points / volume
+        packed, L, O, pfac = mlp.pack(self.sdf_decoder)
+        sdf, u, v = mlp.SdfMlpFunction.apply(pf.reshape(-1, mlp.F), points.reshape(-1, 3), packed, L, O, pfac)
+        gp = torch.autograd.grad(pf, points, u.view_as(pf), create_graph=True, retain_graph=True, only_inputs=True)[0]
+        return sdf.view(*points.shape[:-1], 1), gp + v.view_as(points)
+
     def get_alpha(self, directions, deltas, sdf, gradients):
         inv_s = self.deviation_network.get_variance()
         true_cos = (directions * gradients).sum(-1, keepdim=True)
@@ -181,6 +204,13 @@ class SDFField(nn.Module):
             points = torch.where(points >= 1, torch.full_like(points, 1 - 10e-4), points)
             points = torch.where(points < 0, torch.zeros_like(points), points)
         points = points.detach().requires_grad_(True)
+        if self.mlp_kernel_ok(volume_feature):
+            with torch.enable_grad():
+                sdf, gradients = self._forward_mlp_kernel(points, volume_feature)
+            out = dict(sdf=sdf, gradients=gradients, normal=F.normalize(gradients, dim=-1))
+            if return_alphas:
+                out["alphas"] = self.get_alpha(directions, deltas, sdf, gradients)
+            return out
         with torch.enable_grad():
             sdf, geo, pf = self.get_sdf(points, volume_feature)
             gradients = torch.autograd.grad(sdf, points, torch.ones_like(sdf), create_graph=True, retain_graph=True,
@@ -327,9 +357,11 @@ class NeuSModel(nn.Module):
                      and volume_feature[0].shape[0] == 128)
         can_ray = self.use_ray_kernels and ray.supported(smp.num_samples, smp.num_samples_importance,
                                                          smp.num_upsample_steps)
-        if self.use_fused and not use_fused:
-            _note_once("field", "NeuSModel: this field configuration is not the indoor one the tensor-core field kernels "
-                       "are written for (sdf 64->128->65, rgb 134->128->3, C = 128, share_volume=False); the SDF/colour "
+        self.field.use_mlp_kernel = bool(self.use_fused)
+        if self.use_fused and not use_fused and not self.field.mlp_kernel_ok(volume_feature):
+            _note_once("field", "NeuSModel: this field configuration is neither the indoor one the tensor-core field kernels "
+                       "are written for (sdf 64->128->65, rgb 134->128->3, C = 128, share_volume=False) nor the outdoor "
+                       "one of the fused decoder kernel (sdf 32->16x<=8, shared volume, no colour head); the SDF/colour "
                        "MLPs run as torch linears around the CUDA trilinear sampler")
         if self.use_ray_kernels and not can_ray:
             _note_once("ray", f"NeuSModel: sampler {smp.num_samples}+{smp.num_samples_importance} x "
@@ -357,7 +389,7 @@ class NeuSModel(nn.Module):
                     new_sdf = fused.coarse_sdf(vol_ng, new_pts.reshape(-1, 3), M0_ng, c0_ng, w4_ng, c4_ng).view(
                         new_pts.shape[:-1])
                 else:
-                    new_sdf = self.field.get_sdf(new_pts, volume_feature)[0].squeeze(-1)
+                    new_sdf = self.field.sdf_no_grad(new_pts, volume_feature)
             sdf = new_sdf if sorted_index is None else torch.gather(torch.cat([sdf, new_sdf], -1), 1, sorted_index)
             eu = to_euclid(torch.cat([starts_sp, end_sp], -1))
             alphas = smp.fixed_inv_s_alphas(sdf, eu[:, 1:] - eu[:, :-1], smp.base_variance * 2 ** it)
@@ -466,7 +498,7 @@ class NeuSModel(nn.Module):
         nears, fars, bins, pts_c = ray.ray_setup(o, d, S0, self.collider.bbox, self.collider.near_plane, nz_u)
         rb.nears, rb.fars = nears, fars
         with torch.no_grad():   # coarse pass: un-normalised points, as the reference's sampler calls get_sdf directly
-            sdf_c = fld.get_sdf(pts_c, volume_feature)[0].squeeze(-1)
+            sdf_c = fld.sdf_no_grad(pts_c, volume_feature)
         starts, deltas, pn, init_w, new_bins, minmax = ray.ray_resample(
             o, d, nears, fars, bins, sdf_c, Si, smp.base_variance, nz_p, fld.norm_pts, fld.norm_padding)
         dirs = d[:, None, :].expand(-1, S, -1)

@@ -156,3 +156,96 @@ def test_registry_models_match_reference_state_dicts():
         assert set(got) == set(want[name]), (name, sorted(set(got) ^ set(want[name]))[:10])
         assert all(got[k] == want[name][k] for k in got), name
         assert len(m.grad_completion_order()) == len(list(m.parameters()))
+
+
+def test_sdf_mlp_adjoint_math():
+    """The hand-derived double backward of the fused SDF decoder (csrc/render_mlp.cu, render/mlp.py), restated in torch
+    and checked against autograd in fp64: (sdf, u = d sdf/d f, v = d sdf/d p) and the gradient of an arbitrary scalar
+    of the three with respect to f and every decoder parameter."""
+    torch.manual_seed(0)
+    dt = torch.float64
+    P, F, H, O, L, pf = 50, 32, 16, 17, 6, 1.0
+    Wp, bp = torch.randn(H, 3, dtype=dt) * 0.5, torch.randn(H, dtype=dt) * 0.1
+    Fc = [torch.randn(H, F, dtype=dt) * 0.2 for _ in range(L)]
+    bc = [torch.randn(H, dtype=dt) * 0.1 for _ in range(L)]
+    W = [torch.randn(H if l < L - 1 else O, H, dtype=dt) * 0.3 for l in range(L)]
+    b = [torch.randn(H if l < L - 1 else O, dtype=dt) * 0.1 for l in range(L)]
+    params = [Wp, bp] + Fc + bc + W + b
+    for t in params:
+        t.requires_grad_(True)
+    f = torch.randn(P, F, dtype=dt, requires_grad=True)
+    p = torch.rand(P, 3, dtype=dt, requires_grad=True)
+    sp = lambda y: torch.nn.functional.softplus(y, beta=100)
+    x = pf * (p @ Wp.t() + bp)
+    for l in range(L):
+        y = (x + f @ Fc[l].t() + bc[l]) @ W[l].t() + b[l]
+        if l < L - 1:
+            x = sp(y)
+    sdf = y[:, 0]
+    u, v = torch.autograd.grad(sdf.sum(), [f, p], create_graph=True)
+    gs, gu, gv = torch.randn(P, dtype=dt), torch.randn(P, F, dtype=dt), torch.randn(P, 3, dtype=dt)
+    ref = torch.autograd.grad((sdf * gs).sum() + (u * gu).sum() + (v * gv).sum(), [f] + params)
+    with torch.no_grad():
+        x = pf * (p @ Wp.t() + bp)
+        Z, S = [], []
+        for l in range(L):
+            z = x + f @ Fc[l].t() + bc[l]
+            Z.append(z)
+            if l < L - 1:
+                y = z @ W[l].t() + b[l]
+                S.append(torch.sigmoid(100 * y))
+                x = sp(y)
+        zbar, ybar = [None] * L, [None] * (L - 1)
+        zbar[L - 1] = W[L - 1][0].expand(P, H).clone()
+        um = zbar[L - 1] @ Fc[L - 1]
+        for l in range(L - 2, -1, -1):
+            ybar[l] = zbar[l + 1] * S[l]
+            zbar[l] = ybar[l] @ W[l]
+            um = um + zbar[l] @ Fc[l]
+        vm = pf * (zbar[0] @ Wp)
+        assert torch.allclose(um, u) and torch.allclose(vm, v)
+        D, sbar = [None] * L, [None] * (L - 1)
+        D[0] = gu @ Fc[0].t() + pf * (gv @ Wp.t())
+        for l in range(L - 1):
+            a = D[l] @ W[l].t()
+            sbar[l] = a * zbar[l + 1]
+            D[l + 1] = gu @ Fc[l + 1].t() + a * S[l]
+        zhat = gs[:, None] * W[L - 1][0][None, :]
+        fbar = zhat @ Fc[L - 1]
+        A = [None] * (L - 1)
+        for l in range(L - 2, -1, -1):
+            A[l] = zhat * S[l] + sbar[l] * 100 * S[l] * (1 - S[l])
+            zhat = A[l] @ W[l]
+            fbar = fbar + zhat @ Fc[l]
+        dW, db, dFc, dbc = [None] * L, [None] * L, [None] * L, [None] * L
+        for l in range(L - 1):
+            dW[l] = A[l].t() @ Z[l] + ybar[l].t() @ D[l]
+            db[l] = A[l].sum(0)
+            dFc[l] = W[l].t() @ (A[l].t() @ f + ybar[l].t() @ gu)
+            dbc[l] = W[l].t() @ A[l].sum(0)
+        dW[L - 1] = torch.zeros_like(W[L - 1]); dW[L - 1][0] = gs @ Z[L - 1] + D[L - 1].sum(0)
+        db[L - 1] = torch.zeros_like(b[L - 1]); db[L - 1][0] = gs.sum()
+        dFc[L - 1] = torch.outer(W[L - 1][0], gs @ f + gu.sum(0))
+        dbc[L - 1] = W[L - 1][0] * gs.sum()
+        dWp = pf * (W[0].t() @ (A[0].t() @ p + ybar[0].t() @ gv))
+        dbp = pf * (W[0].t() @ A[0].sum(0))
+        man = [fbar, dWp, dbp] + dFc + dbc + dW + db
+    for i, (m_, r_) in enumerate(zip(man, ref)):
+        e = ((m_ - r_).norm() / r_.norm().clamp(min=1e-30)).item()
+        assert e < 1e-6, (i, e)
+
+
+def test_sdf_mlp_pack_layout():
+    """render.mlp.pack lays the decoder's parameters out as the kernels (pv2_sdf_mlp_param_count) expect."""
+    from ponderv2_b200 import _lib
+    from ponderv2_b200.render import mlp
+    from ponderv2_b200.render.neus import SDFDecoder
+    dec = SDFDecoder(in_dim=32, out_dim=17, hidden_size=16, n_blocks=5)
+    packed, L, O, pf = mlp.pack(dec)
+    assert (L, O, pf) == (6, 17, 1.0)
+    assert packed.numel() == _lib.load().pv2_sdf_mlp_param_count(L, O) == 4881
+    assert torch.equal(packed[:48], dec.fc_p.weight.detach().reshape(-1))
+    assert torch.equal(packed[64:64 + 512], dec.fc_c[0].weight.detach().reshape(-1))
+    assert torch.equal(packed[-17:], dec.lin5.bias.detach())
+    packed.sum().backward()
+    assert all(q.grad is not None for q in dec.parameters())
