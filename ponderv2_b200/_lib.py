@@ -106,19 +106,52 @@ def check(code: int, what: str) -> None:
 
 
 def ptr(t):
-    """Device pointer of a torch tensor (None -> NULL).  The tensor must be CUDA + contiguous."""
+    """Device pointer of a torch tensor (None -> NULL) as a plain int (ctypes converts it for `c_void_p` parameters).
+    The tensor must be CUDA + contiguous."""
     if t is None:
         return None
     if not t.is_cuda:
         raise RuntimeError("ponderv2_b200 kernels need CUDA tensors (there is no CPU fallback)")
     if not t.is_contiguous():
         raise RuntimeError("ponderv2_b200 kernels need contiguous tensors")
-    return C.c_void_p(t.data_ptr())
+    return t.data_ptr()
+
+
+_torch_C = None
+
+
+def _tc():
+    global _torch_C
+    if _torch_C is None:
+        import torch
+        _torch_C = torch._C
+    return _torch_C
 
 
 def stream_ptr():
+    """cudaStream_t of torch's current stream on the current device, as an int.  The wrappers ask ~400 times per step:
+    `torch.cuda.current_stream()` builds a Stream object through several Python layers (13 us measured, 7 ms per
+    step, profiles/r2k_host_profile.txt); the raw query is one C call."""
+    tc = _tc()
+    return tc._cuda_getCurrentRawStream(tc._cuda_getDevice())
+
+
+_WS = {}
+
+
+def workspace(nbytes: int, device):
+    """Scratch of at least `nbytes` for a kernel launched on the CURRENT stream of `device`: one growing buffer per
+    (device, stream), so back-to-back calls do not go through the allocator (stream order makes the reuse safe; a
+    different stream gets a different buffer).  None for nbytes == 0."""
+    if nbytes <= 0:
+        return None
     import torch
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    key = (device.index, stream_ptr())
+    buf = _WS.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _WS[key] = buf
+    return buf
 
 
 def i32x3(vals):
@@ -185,9 +218,9 @@ _NULL = _NullCtx()
 def on_device(dev):
     """`with on_device(t.device):` — torch.cuda.device(dev) only when `dev` is not already current (the context manager
     costs two driver calls per entry; the wrappers are entered ~1000 times per step)."""
-    import torch
-    if dev.index is None or torch.cuda.current_device() == dev.index:
+    if dev.index is None or _tc()._cuda_getDevice() == dev.index:
         return _NULL
+    import torch
     return torch.cuda.device(dev)
 
 

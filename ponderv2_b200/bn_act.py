@@ -29,8 +29,8 @@ class _BNActFunction(torch.autograd.Function):
         y = torch.empty_like(x)
         stats = torch.empty((2, c), dtype=torch.float32, device=dev)
         ws_bytes = lib.pv2_bn_workspace_bytes(n, c)
-        ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
         with _lib.on_device(dev):
+            ws = _lib.workspace(max(ws_bytes, 16), dev)
             _lib.check(lib.pv2_bn_act_fwd_t(_lib.ptr(x), _lib.ptr(res_c), _lib.ptr(gamma.contiguous()),
                                             _lib.ptr(beta.contiguous()), _lib.ptr(running_mean), _lib.ptr(running_var),
                                             float(momentum), float(eps), int(relu), n, c, _lib.ptr(y), _lib.ptr(stats[0]),
@@ -62,8 +62,8 @@ class _BNActFunction(torch.autograd.Function):
             dgb = torch.empty((2, c), dtype=torch.float32, device=dev)
             dg_t, db_t, acc = dgb[0], dgb[1], 0
         ws_bytes = lib.pv2_bn_workspace_bytes(n, c)
-        ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
         with _lib.on_device(dev):
+            ws = _lib.workspace(max(ws_bytes, 16), dev)
             _lib.check(lib.pv2_bn_act_bwd_t(_lib.ptr(x), _lib.ptr(dy), _lib.ptr(y), _lib.ptr(gamma.contiguous()),
                                             _lib.ptr(stats[0]), _lib.ptr(stats[1]), int(ctx.relu), n, c, _lib.ptr(dx),
                                             _lib.ptr(dres), _lib.ptr(dg_t), _lib.ptr(db_t), acc, _lib.dtype_code(x.dtype),

@@ -26,9 +26,9 @@ from .. import _lib
 def _linear(x, x_row, x_lo, presplit, w, bias, y, y_row, y_lo, y_split, act, y2, y2_row, y2_lo, rows, cin, cout):
     lib = _lib.load()
     ws_bytes = lib.pv2_linear_workspace_bytes(rows, cin, cout, int(presplit))
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=w.device)
     w = w.contiguous()
     with _lib.on_device(w.device):
+        ws = _lib.workspace(ws_bytes, w.device)
         _lib.check(lib.pv2_linear(_lib.C.c_void_p(x.data_ptr()), x_row, x_lo, int(presplit), _lib.ptr(w),
                                   _lib.ptr(bias.contiguous()) if bias is not None else None,
                                   _lib.C.c_void_p(y.data_ptr()), y_row, y_lo, int(y_split), act,

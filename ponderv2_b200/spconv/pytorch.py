@@ -174,8 +174,8 @@ def _gather_gemm(x: torch.Tensor, w3: torch.Tensor, bias: Optional[torch.Tensor]
     nbytes = x.shape[0] * cin * b + n_out * cout * b + kvol * cin * cout * b + 4 * kvol * n_out
     dcode = _lib.dtype_code(x.dtype)
     ws_bytes = lib.pv2_spconv_workspace_bytes(x.shape[0], cin, cout, kvol, dcode)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes else None
     with _lib.on_device(x.device), _lib.timed("pv2_spconv_gather_gemm", nbytes, 0):
+        ws = _lib.workspace(ws_bytes, x.device)
         _lib.check(lib.pv2_spconv_gather_gemm(_lib.ptr(x), _lib.C.c_void_p(w3.data_ptr()), w3.stride(0), w3.stride(1),
                                               _lib.ptr(bias), _lib.ptr(nbr), _lib.ptr(order), _lib.ptr(y), x.shape[0],
                                               n_out, cin,
@@ -205,8 +205,8 @@ def _wgrad(x: torch.Tensor, dy: torch.Tensor, tmap: TileMap, kvol: int, out: Opt
     b = x.element_size()
     nbytes = x.shape[0] * cin * b + dy.shape[0] * cout * b + kvol * cin * cout * 4 + 4 * kvol * dy.shape[0]
     ws_bytes = lib.pv2_wgrad_workspace_bytes(x.shape[0], dy.shape[0], cin, cout) if x.dtype == torch.float32 else 0
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes else None
     with _lib.on_device(x.device), _lib.timed("pv2_spconv_wgrad", nbytes, 0):
+        ws = _lib.workspace(ws_bytes, x.device)
         _lib.check(lib.pv2_spconv_wgrad(_lib.ptr(x.contiguous()), _lib.ptr(dy.contiguous()), _lib.ptr(nbr),
                                         _lib.ptr(order), _lib.ptr(tmap.blk_active), _lib.ptr(dw), x.shape[0],
                                         dy.shape[0], cin, cout, kvol,
