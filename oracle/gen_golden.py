@@ -217,6 +217,49 @@ def gen_spunet_state() -> None:
     print(f"spunet_v1m1_state: {len(state)} entries, {n_conv} conv parameters")
 
 
+def gen_pdnorm() -> None:
+    """SpUNet-v1m3 (spconv_unet_v1m3_pdnorm.py): (1) state_dict names + shapes of the reference class built on the aliased
+    spconv modules; (2) the reference `PDBatchNorm` (pure torch, CPU) in training mode on random features: output, running
+    buffers and gradients w.r.t. features, context and modulation parameters, for the decoupled + adaptive, non-affine
+    configuration the PPT configs use and the affine, non-adaptive default."""
+    from ponder.models.sparse_unet.spconv_unet_v1m3_pdnorm import PDBatchNorm, SpUNetBase
+
+    torch.manual_seed(0)
+    m = SpUNetBase(in_channels=6, num_classes=0, conditions=("ScanNet", "S3DIS", "Structured3D"))
+    state = {k: list(v.shape) for k, v in m.state_dict().items()}
+    (GOLD / "spunet_v1m3_state.json").write_text(json.dumps({"state": state}, indent=0))
+    arrays = {}
+    for tag, kw in (("adaptive", dict(decouple=True, adaptive=True, affine=False)),
+                    ("affine", dict(decouple=True, adaptive=False, affine=True)),
+                    ("both", dict(decouple=False, adaptive=True, affine=True))):
+        torch.manual_seed(11)
+        n, c, cc = 777, 32, 16
+        pd = PDBatchNorm(c, context_channels=cc, conditions=("A", "B"), **kw).train()
+        with torch.no_grad():
+            for p_ in pd.parameters():
+                p_.copy_(torch.randn_like(p_) * 0.3 + (1.0 if p_.dim() == 1 and kw["affine"] and p_.numel() == c else 0.0))
+        x = (torch.randn(n, c) * 2.0 + 0.5).requires_grad_(True)
+        ctx = torch.randn(1, cc).requires_grad_(True)
+        sd0 = {k: v.clone() for k, v in pd.state_dict().items()}
+        y = pd(x, "B", ctx if kw["adaptive"] else None)
+        go = torch.randn(n, c)
+        (y * go).sum().backward()
+        arrays.update({f"{tag}.x": x.detach(), f"{tag}.ctx": ctx.detach(), f"{tag}.go": go, f"{tag}.y": y.detach(),
+                       f"{tag}.dx": x.grad})
+        if kw["adaptive"]:
+            arrays[f"{tag}.dctx"] = ctx.grad
+        for k, v in sd0.items():
+            arrays[f"{tag}.param.{k}"] = v
+        for k, v in pd.state_dict().items():
+            if "running" in k:
+                arrays[f"{tag}.after.{k}"] = v
+        for k, p_ in pd.named_parameters():
+            if p_.grad is not None:
+                arrays[f"{tag}.grad.{k}"] = p_.grad
+    np.savez_compressed(GOLD / "pdnorm.npz", **{k: v.numpy() for k, v in arrays.items()})
+    print(f"spunet_v1m3_state: {len(state)} entries; pdnorm.npz: {len(arrays)} arrays")
+
+
 def gen_rayprep_case() -> None:
     """Golden vectors of the indoor ray preparation: the reference's own `PonderIndoor.to_unit_cube`, `ray_sample` and
     `grid_sample` (ponder_indoor_base.py:344-633) run on a small synthetic collate dict (2 scenes, 2 views of 12 x 16
@@ -345,6 +388,8 @@ def main() -> None:
         gen_render_case(name, spec, Dict)
     if not only or "spunet_state" in only:
         gen_spunet_state()
+    if not only or "pdnorm" in only:
+        gen_pdnorm()
     if not only or "rayprep" in only:
         gen_rayprep_case()
     if not only or "models" in only:

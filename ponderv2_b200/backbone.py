@@ -77,6 +77,27 @@ class ConvBNReLU(spconv.SparseSequential):
         return out.replace_feature(bn_act(out.features, self[1], None, True))
 
 
+def prebuild_rulebooks(x: "spconv.SparseConvTensor", stem_kernel: int, num_stages: int) -> None:
+    """All coordinate work of the step up front.  The rulebooks depend on coordinates only, and each strided one
+    ends in a host read of its output count (tensor shapes depend on it); built lazily inside the layer stack
+    those four syncs drain a full launch queue each.  Built here, nothing is queued behind them yet and the host
+    runs ahead of the GPU for the rest of the forward pass.  Keys are the reference's indice_keys
+    (spconv_unet_v1m1_base.py:111-177): stem (k5), subm0..4 (k3), spconv1..4 (k2 s2)."""
+    d = x.indice_dict
+    ind, shape = x.indices, x.spatial_shape
+    if "stem" not in d:
+        d["stem"] = spconv.build_subm_rulebook(ind, shape, stem_kernel, count_pairs=False)
+    if "subm0" not in d:
+        d["subm0"] = spconv.build_subm_rulebook(ind, shape, 3, count_pairs=False)
+    for s in range(num_stages):
+        key = f"spconv{s + 1}"
+        if key not in d:
+            d[key] = spconv.build_down_rulebook(ind, shape)
+        ind, shape = d[key].out_indices, d[key].out_shape
+        if f"subm{s + 1}" not in d:
+            d[f"subm{s + 1}"] = spconv.build_subm_rulebook(ind, shape, 3, count_pairs=False)
+
+
 class SpUNetBase(nn.Module):
     def __init__(self, in_channels, num_classes, base_channels=32, channels=(32, 64, 128, 256, 256, 128, 96, 96),
                  layers=(2, 3, 4, 6, 2, 2, 2, 2), cls_mode=False):
@@ -129,24 +150,7 @@ class SpUNetBase(nn.Module):
             nn.init.constant_(m.weight, 1.0)
 
     def _prebuild_rulebooks(self, x: "spconv.SparseConvTensor") -> None:
-        """All coordinate work of the step up front.  The rulebooks depend on coordinates only, and each strided one
-        ends in a host read of its output count (tensor shapes depend on it); built lazily inside the layer stack
-        those four syncs drain a full launch queue each.  Built here, nothing is queued behind them yet and the host
-        runs ahead of the GPU for the rest of the forward pass.  Keys are the reference's indice_keys
-        (spconv_unet_v1m1_base.py:111-177): stem (k5), subm0..4 (k3), spconv1..4 (k2 s2)."""
-        d = x.indice_dict
-        ind, shape = x.indices, x.spatial_shape
-        if "stem" not in d:
-            d["stem"] = spconv.build_subm_rulebook(ind, shape, self.conv_input[0].kernel_size[0], count_pairs=False)
-        if "subm0" not in d:
-            d["subm0"] = spconv.build_subm_rulebook(ind, shape, 3, count_pairs=False)
-        for s in range(self.num_stages):
-            key = f"spconv{s + 1}"
-            if key not in d:
-                d[key] = spconv.build_down_rulebook(ind, shape)
-            ind, shape = d[key].out_indices, d[key].out_shape
-            if f"subm{s + 1}" not in d:
-                d[f"subm{s + 1}"] = spconv.build_subm_rulebook(ind, shape, 3, count_pairs=False)
+        prebuild_rulebooks(x, self.conv_input[0].kernel_size[0], self.num_stages)
 
     def forward(self, input_dict):
         grid_coord, feat, offset = input_dict["grid_coord"], input_dict["feat"], input_dict["offset"]

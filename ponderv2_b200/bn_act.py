@@ -92,6 +92,46 @@ def supported(x: torch.Tensor, bn: nn.BatchNorm1d) -> bool:
             and x.shape[1] % 4 == 0 and x.shape[1] <= 1024 and bn.affine and bn.weight.dtype == torch.float32)
 
 
+def supported_modulated(x: torch.Tensor) -> bool:
+    return (x.is_cuda and x.dtype in (torch.float32, torch.bfloat16) and x.dim() == 2 and x.shape[0] > 1
+            and x.shape[1] % 4 == 0 and x.shape[1] <= 1024)
+
+
+def bn_act_modulated(x: torch.Tensor, bn: nn.BatchNorm1d, scale: Optional[torch.Tensor], shift: Optional[torch.Tensor],
+                     residual: Optional[torch.Tensor] = None, relu: bool = True) -> torch.Tensor:
+    """relu(bn(x) * (1 + scale) + shift + residual) — prompt-driven normalisation (PDBatchNorm.forward,
+    spconv_unet_v1m3_pdnorm.py:60-72) folded into the fused kernels: with per-channel `scale`, `shift` ([C] or [1, C],
+    differentiable, produced by the context modulation) the map is a BatchNorm whose affine pair is
+    gamma' = gamma (1 + scale), beta' = beta (1 + scale) + shift, so the same two kernels run and autograd carries
+    dgamma' / dbeta' back into the modulation Linear (and into gamma / beta when `bn.affine`)."""
+    c = x.shape[1]
+    one_plus = (1.0 + scale.reshape(c).float()) if scale is not None else None
+    if bn.affine:
+        gamma = bn.weight * one_plus if one_plus is not None else bn.weight
+        beta = bn.bias * one_plus if one_plus is not None else bn.bias
+    else:
+        gamma = one_plus if one_plus is not None else torch.ones(c, dtype=torch.float32, device=x.device)
+        beta = torch.zeros(c, dtype=torch.float32, device=x.device)
+    if shift is not None:
+        beta = beta + shift.reshape(c).float()
+    if bn.training and supported_modulated(x):
+        momentum = bn.momentum
+        if bn.track_running_stats and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+            if momentum is None:
+                momentum = 1.0 / float(bn.num_batches_tracked)
+        rm = bn.running_mean if bn.track_running_stats else None
+        rv = bn.running_var if bn.track_running_stats else None
+        return _BNActFunction.apply(x, residual, gamma, beta, rm, rv, float(momentum or 0.0), float(bn.eps), relu)
+    if x.is_cuda:
+        _note_fallback(x, bn)
+    out = F.batch_norm(x, bn.running_mean, bn.running_var, None, None, bn.training, bn.momentum or 0.0, bn.eps)
+    out = out * gamma.to(out.dtype) + beta.to(out.dtype)
+    if residual is not None:
+        out = out + residual
+    return F.relu(out) if relu else out
+
+
 def bn_act(x: torch.Tensor, bn: nn.BatchNorm1d, residual: Optional[torch.Tensor] = None, relu: bool = True) -> torch.Tensor:
     """relu(bn(x) + residual) with `bn` an nn.BatchNorm1d (its parameters and running buffers are used / updated)."""
     if bn.training and supported(x, bn):

@@ -1,6 +1,7 @@
 """Registry-facing model classes (boundary B3): the reference's `MODELS` / `RENDERERS` names on the B200 path.
 
     "SpUNet-v1m1"        ponder/models/sparse_unet/spconv_unet_v1m1_base.py:86      -> backbone.SpUNetBase
+    "SpUNet-v1m3"        ponder/models/sparse_unet/spconv_unet_v1m3_pdnorm.py:246  -> backbone_pdnorm.SpUNetPDNorm (§8f-3)
     "SimpleConv3D-v1m1"  ponder/models/ponder/unet3d.py:16                          -> pretrain.SimpleConv3D
     "UNet3D-v1m2"        ponder/models/ponder/unet3d.py:710 (Abstract3DUNet :530)   -> UNet3Dv1m2 (dense, cuDNN; §8f-1)
     "PonderIndoor-v2"    ponder/models/ponder/ponder_indoor_base.py:19              -> PonderIndoor
@@ -23,6 +24,7 @@ from torch import nn
 
 from . import rayprep
 from .backbone import SpUNetBase
+from .backbone_pdnorm import SpUNetPDNorm
 from .pretrain import PonderIndoorStep, PonderOutdoorStep, SimpleConv3D, _SceneViews
 from .render import RayBundle
 from .render.neus import NeuSModel
@@ -65,6 +67,7 @@ class Registry:
 MODELS = Registry("models")
 RENDERERS = Registry("renderers")
 MODELS.register_module("SpUNet-v1m1", module=SpUNetBase)
+MODELS.register_module("SpUNet-v1m3", module=SpUNetPDNorm)
 MODELS.register_module("SimpleConv3D-v1m1", module=SimpleConv3D)
 RENDERERS.register_module("NeuSModel", module=NeuSModel)
 
@@ -193,6 +196,9 @@ class PonderIndoor(PonderIndoorStep):
         if self.mask is not None:
             data_dict["feat"] = self.mask_features(data_dict["grid_coord"], data_dict["feat"], data_dict["offset"],
                                                    noise.get("mask"))
+        if "condition" in data_dict and self.conditions is not None:                     # PPT context row (:164-172)
+            idx = self.conditions.index(data_dict["condition"][0])
+            data_dict["context"] = self.embedding_table.weight[idx:idx + 1]
         data_dict["sparse_backbone_feat"] = self.backbone(data_dict)                     # extract_feature
         cube = rayprep.to_unit_cube(data_dict)                                           # prepare_ray
         ray = rayprep.ray_sample(cube, self.ray_nsample, self.bounds, pixels=noise.get("pixels"))
@@ -258,6 +264,6 @@ def install_into_reference() -> None:
     sys.modules.setdefault("smooth_sampler", _ss)
     from ponder.models.builder import MODELS as REF_MODELS                      # noqa: E402  (the reference)
     from ponder.models.ponder.render_utils.builder import RENDERERS as REF_RENDERERS
-    for name in ("SpUNet-v1m1", "SimpleConv3D-v1m1", "UNet3D-v1m2", "PonderIndoor-v2", "PonderOutdoor-v2"):
+    for name in ("SpUNet-v1m1", "SpUNet-v1m3", "SimpleConv3D-v1m1", "UNet3D-v1m2", "PonderIndoor-v2", "PonderOutdoor-v2"):
         REF_MODELS.register_module(name=name, force=True, module=MODELS.get(name))
     REF_RENDERERS.register_module(name="NeuSModel", force=True, module=NeuSModel)

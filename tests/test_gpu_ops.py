@@ -281,6 +281,118 @@ def test_spunet_state_dict_contract(cuda_lib):
     assert got == want
 
 
+# ------------------------------------------------------------------------------------------ SpUNet-v1m3 (PDNorm, §8f-3)
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ["adaptive", "affine", "both"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_pdnorm_fused_matches_reference_golden(cuda_lib, tag, dtype):
+    """PDBatchNorm on the fused BN kernels (context modulation folded into the affine pair) against the reference
+    module's output, running buffers and gradients (tests/golden/pdnorm.npz, generated by the imported reference)."""
+    from pathlib import Path
+    from ponderv2_b200.backbone_pdnorm import PDBatchNorm
+    dev = _dev()
+    g = np.load(Path(__file__).parent / "golden" / "pdnorm.npz")
+    kw = dict(adaptive=dict(decouple=True, adaptive=True, affine=False), affine=dict(decouple=True, adaptive=False, affine=True),
+              both=dict(decouple=False, adaptive=True, affine=True))[tag]
+    pd = PDBatchNorm(32, context_channels=16, conditions=("A", "B"), **kw).train()
+    pd.load_state_dict({k[len(tag) + 7:]: torch.from_numpy(g[k]) for k in g.files if k.startswith(tag + ".param.")})
+    pd = pd.to(dev)
+    x = torch.from_numpy(g[f"{tag}.x"]).to(dev, dtype).requires_grad_(True)
+    ctx = torch.from_numpy(g[f"{tag}.ctx"]).to(dev).requires_grad_(True)
+    y = pd(x, "B", ctx if kw["adaptive"] else None)
+    assert y.dtype == dtype
+    (y.float() * torch.from_numpy(g[f"{tag}.go"]).to(dev)).sum().backward()
+    lo = dtype == torch.bfloat16
+    rel = lambda a, b: float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-12))
+    errs = dict(y=rel(y.detach().float().cpu().numpy(), g[f"{tag}.y"]), dx=rel(x.grad.float().cpu().numpy(), g[f"{tag}.dx"]))
+    if kw["adaptive"]:
+        errs["dctx"] = rel(ctx.grad.cpu().numpy(), g[f"{tag}.dctx"])
+    for k, p in pd.named_parameters():
+        if f"{tag}.grad.{k}" in g.files:
+            errs["grad." + k] = rel(p.grad.cpu().numpy(), g[f"{tag}.grad.{k}"])
+    for k, v in pd.state_dict().items():
+        if "running" in k:
+            errs["after." + k] = rel(v.cpu().numpy(), g[f"{tag}.after.{k}"])
+    from tests.conftest import record
+    record("pdnorm_fused", tag=tag, dtype=str(dtype), **errs)
+    tol = 1.2e-2 if lo else 2e-5     # bf16: input and output rounding (2^-9 each) of unit-scale features
+    for k, e in errs.items():
+        assert e < tol, (k, e, errs)
+
+
+@pytest.mark.gpu
+def test_spunet_v1m3_matches_oracle(cuda_lib):
+    """Whole SpUNet-v1m3 with a NON-trivial context modulation on a 6 k-voxel two-scene batch.  Per norm layer the
+    modulation is a per-channel affine map, so the network equals SpUNet-v1m1 with BatchNorm weight = 1 + scale and
+    bias = shift: the fp64 oracle (oracle/spconv_oracle.py:spunet_forward) is run on that translated state dict and
+    compared in output, conv-weight gradients and modulation-bias gradients (= [d shift, d scale] = the oracle's
+    [d bias, d weight])."""
+    from ponderv2_b200.backbone_pdnorm import PDBatchNorm, SpUNetPDNorm
+    dev = _dev()
+    torch.manual_seed(5)
+    a, b = synth.indoor_cloud(3600, 31), synth.indoor_cloud(2400, 32)
+    gc = np.concatenate([a["grid_coord"], b["grid_coord"]])
+    feat = np.concatenate([a["feat"], b["feat"]])
+    offset = np.array([3600, 6000], dtype=np.int64)
+    model = SpUNetPDNorm(in_channels=6, num_classes=0, context_channels=24, conditions=("ScanNet", "S3DIS"),
+                         zero_init=False).train()
+    with torch.no_grad():
+        for k, p in model.named_parameters():
+            if "modulation" in k:
+                p.copy_(torch.randn_like(p) * 0.15)
+    model = model.to(dev)
+    context = torch.randn(1, 24)
+    # translate to the v1m1 oracle's state dict
+    names = {"conv_input.conv.": "conv_input.0.", "conv_input.bn": "conv_input.1"}
+    def v1(k):
+        k = k.replace("conv_input.conv.", "conv_input.0.").replace(".proj_conv.", ".proj.0.")
+        for pre in ("down", "up"):
+            for s in range(4):
+                k = k.replace(f"{pre}.{s}.conv.", f"{pre}.{s}.0.")
+        return k
+    sd, norm_of = {}, {}
+    for k, p in model.named_parameters():
+        if k.endswith(".weight") and p.dim() == 5:
+            sd[v1(k)] = p.detach().cpu().double().requires_grad_(True)
+    for name, m in model.named_modules():
+        if isinstance(m, PDBatchNorm):
+            shift, scale = m.modulation(context.to(dev)).detach().cpu().double().chunk(2, dim=1)
+            tgt = name.replace("conv_input.bn", "conv_input.1").replace(".proj_norm", ".proj.1")
+            for pre in ("down", "up"):
+                for s in range(4):
+                    if tgt == f"{pre}.{s}.bn":
+                        tgt = f"{pre}.{s}.1"
+            sd[tgt + ".weight"] = (1.0 + scale[0]).requires_grad_(True)
+            sd[tgt + ".bias"] = shift[0].clone().requires_grad_(True)
+            norm_of[name] = tgt
+    out = model({"grid_coord": torch.from_numpy(gc).to(dev), "feat": torch.from_numpy(feat).to(dev),
+                 "offset": torch.from_numpy(offset).to(dev), "condition": ["S3DIS"], "context": context.to(dev)})
+    ref = so.spunet_forward(sd, gc, torch.from_numpy(feat).double(), offset)
+    err = (out.detach().cpu().double() - ref.detach()).abs().max().item() / ref.abs().max().item()
+    assert err < 5e-4, err
+    gr = torch.randn(ref.shape, dtype=torch.float64, generator=torch.Generator().manual_seed(1))
+    ref.backward(gr)
+    out.backward(gr.to(dev, torch.float32))
+    num = den = 0.0
+    for k, p in model.named_parameters():
+        if k.endswith(".weight") and p.dim() == 5:
+            rg = sd[v1(k)].grad
+        elif k.endswith("modulation.1.bias"):
+            tgt = norm_of[k[:-len(".modulation.1.bias")]]
+            rg = torch.cat([sd[tgt + ".bias"].grad, sd[tgt + ".weight"].grad])
+        else:
+            continue
+        d = p.grad.cpu().double() - rg
+        num += d.pow(2).sum().item(); den += rg.pow(2).sum().item()
+    joint = (num / den) ** 0.5
+    # the unused condition's BatchNorms must be untouched (decoupled statistics)
+    bn_other = model.conv_input.bn.bns[0]
+    assert int(bn_other.num_batches_tracked) == 0 and int(model.conv_input.bn.bns[1].num_batches_tracked) == 1
+    from tests.conftest import record
+    record("spunet_v1m3_matches_oracle", fwd=err, grad_joint=joint)
+    assert joint < 1.5e-2, joint
+
+
 # ------------------------------------------------------------------------------------------ densify
 def test_densify_indoor_and_outdoor(cuda_lib):
     from ponderv2_b200 import densify

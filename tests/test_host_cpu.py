@@ -249,3 +249,54 @@ def test_sdf_mlp_pack_layout():
     assert torch.equal(packed[-17:], dec.lin5.bias.detach())
     packed.sum().backward()
     assert all(q.grad is not None for q in dec.parameters())
+
+
+# ------------------------------------------------------------------------------------------ SpUNet-v1m3 (PDNorm, §8f-3)
+def _pdnorm_case(tag):
+    from pathlib import Path
+    from ponderv2_b200.backbone_pdnorm import PDBatchNorm
+    g = np.load(Path(__file__).parent / "golden" / "pdnorm.npz")
+    kw = dict(adaptive=dict(decouple=True, adaptive=True, affine=False), affine=dict(decouple=True, adaptive=False, affine=True),
+              both=dict(decouple=False, adaptive=True, affine=True))[tag]
+    pd = PDBatchNorm(32, context_channels=16, conditions=("A", "B"), **kw).train()
+    sd = {k[len(tag) + 7:]: torch.from_numpy(g[k]) for k in g.files if k.startswith(tag + ".param.")}
+    pd.load_state_dict(sd)
+    return g, kw, pd
+
+
+def test_pdnorm_folding_matches_reference_golden():
+    """The folding of the context modulation into the BatchNorm affine pair (bn_act.bn_act_modulated; here its torch
+    branch, the algebra the fused kernels are handed) against the reference PDBatchNorm's output, running buffers and
+    gradients (tests/golden/pdnorm.npz, oracle/gen_golden.py:gen_pdnorm)."""
+    for tag in ("adaptive", "affine", "both"):
+        g, kw, pd = _pdnorm_case(tag)
+        x = torch.from_numpy(g[f"{tag}.x"]).requires_grad_(True)
+        ctx = torch.from_numpy(g[f"{tag}.ctx"]).requires_grad_(True)
+        y = pd(x, "B", ctx if kw["adaptive"] else None)
+        (y * torch.from_numpy(g[f"{tag}.go"])).sum().backward()
+        np.testing.assert_allclose(y.detach().numpy(), g[f"{tag}.y"], rtol=1e-5, atol=2e-5)
+        np.testing.assert_allclose(x.grad.numpy(), g[f"{tag}.dx"], rtol=1e-4, atol=2e-5)
+        if kw["adaptive"]:
+            np.testing.assert_allclose(ctx.grad.numpy(), g[f"{tag}.dctx"], rtol=1e-4, atol=1e-3)
+        for k, p in pd.named_parameters():
+            key = f"{tag}.grad.{k}"
+            if key in g.files:
+                np.testing.assert_allclose(p.grad.numpy(), g[key], rtol=1e-4, atol=2e-3)
+        for k, v in pd.state_dict().items():
+            if "running" in k:
+                np.testing.assert_allclose(v.numpy(), g[f"{tag}.after.{k}"], rtol=1e-5, atol=1e-6)
+
+
+def test_spunet_v1m3_state_dict_contract():
+    """Parameter / buffer names and shapes equal the reference's SpUNet-v1m3 (PPT checkpoints load unchanged), through
+    the registry name."""
+    import json
+    from pathlib import Path
+    from ponderv2_b200.models import MODELS
+    want = json.loads((Path(__file__).parent / "golden" / "spunet_v1m3_state.json").read_text())["state"]
+    m = MODELS.build(dict(type="SpUNet-v1m3", in_channels=6, num_classes=0,
+                          conditions=("ScanNet", "S3DIS", "Structured3D")))
+    got = {k: list(v.shape) for k, v in m.state_dict().items()}
+    assert got == want
+    # zero_init: the modulation starts as the identity
+    assert all(float(p.abs().max()) == 0.0 for k, p in m.named_parameters() if "modulation" in k)
