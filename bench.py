@@ -339,7 +339,7 @@ def run_reference(args, wl: dict) -> None:
 
 
 # ------------------------------------------------------------------------------------------------------------
-def build_model(wl: dict, dev):
+def build_model(wl: dict, dev, overlap: bool = True):
     """Model (identical replicas: fixed seed), flat parameter/gradient buffers, SGD as in the reference configs
     (configs/scannet/pretrain-ponder-spunet-v1m1-0-base.py:96-98)."""
     from ponderv2_b200.dist import FlatParameters, broadcast_parameters
@@ -359,7 +359,8 @@ def build_model(wl: dict, dev):
     flat = FlatParameters(model, order=model.grad_completion_order(), num_chunks=4)
     flat.freeze_untouched([n for n, _ in model.named_parameters() if "laplace_density" in n])
     broadcast_parameters(flat)
-    flat.enable_overlap()
+    if overlap:
+        flat.enable_overlap()
     opt = flat.make_optimizer(torch.optim.SGD, lr=5e-4, momentum=0.9, weight_decay=1e-4, nesterov=True)
     return model, flat, opt
 
@@ -368,12 +369,22 @@ def nccl_summary(path_glob: str) -> dict:
     """Algorithm / protocol / transport lines NCCL logged for the all-reduce (NCCL_DEBUG=INFO to per-rank files)."""
     import glob
     import re
-    found = {"nvls": False, "channels": None, "algos": set(), "version": None}
-    for f in glob.glob(path_glob):
+    found = {"nvls": False, "channels": None, "algos": set(), "version": None, "ranks_logged": 0, "lines": []}
+    for f in sorted(glob.glob(path_glob)):
         try:
             txt = Path(f).read_text(errors="ignore")
         except OSError:
             continue
+        found["ranks_logged"] += 1
+        if not found["lines"]:   # a few verbatim lines of one rank: transport, channel count, tuning choice
+            keep = [ln.split(" NCCL INFO ", 1)[-1][:160] for ln in txt.splitlines()
+                    if re.search(r"NVLS|coll channels|via P2P|Connected all|AllReduce.*(Algo|algo)|comm 0x.* rank .* nranks", ln)]
+            seen, uniq = set(), []
+            for ln in keep:
+                key = re.sub(r"0x[0-9a-f]+|\d+", "#", ln)
+                if key not in seen:
+                    seen.add(key); uniq.append(ln)
+            found["lines"] = uniq[:12]
         if re.search(r"NVLS", txt):
             found["nvls"] = True
         m = re.search(r"NCCL version ([0-9.+a-z]+)", txt)
@@ -407,13 +418,14 @@ def run_ours(args, wl: dict) -> None:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # NCCL's INFO log (algorithm, channels, NVLS) goes to per-rank files, never to the JSON line on stdout
         nccl_log = tempfile.mkdtemp(prefix="pv2_nccl_")
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,COLL,TUNING")
-        os.environ.setdefault("NCCL_DEBUG_FILE", os.path.join(nccl_log, "rank%h.%p.log"))
+        # (forced, not setdefault: with an inherited NCCL_DEBUG=VERSION/WARN NCCL printf's its version line to stdout)
+        os.environ["NCCL_DEBUG"] = "INFO"
+        os.environ["NCCL_DEBUG_SUBSYS"] = "INIT,GRAPH,TUNING"
+        os.environ["NCCL_DEBUG_FILE"] = os.path.join(nccl_log, "rank%h.%p.log")
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
 
-    model, flat, opt = build_model(wl, dev)
+    model, flat, opt = build_model(wl, dev, overlap=not args.no_overlap)
     autocast = (lambda: torch.autocast("cuda", dtype=torch.bfloat16)) if wl["dtype"] == "bf16" else \
                (lambda: torch.autocast("cuda", enabled=False))
 
@@ -542,6 +554,11 @@ def run_ours(args, wl: dict) -> None:
         }
         if nccl_log is not None:
             line["nccl"] = nccl_summary(os.path.join(nccl_log, "*.log"))
+            line["nccl"]["overlap"] = not args.no_overlap
+            if os.environ.get("PV2_NCCL_LOG_COPY"):      # dev switch: keep the raw per-rank NCCL logs
+                import shutil
+                shutil.copytree(nccl_log, os.environ["PV2_NCCL_LOG_COPY"], dirs_exist_ok=True)
+            log("nccl: " + json.dumps(line["nccl"]))
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -555,6 +572,9 @@ def main() -> None:
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true",
+                    help="N > 1: one all-reduce of the whole flat gradient buffer after backward instead of chunked "
+                         "all-reduces overlapped with it (A/B switch)")
     ap.add_argument("--profile-step", action="store_true",
                     help="run one warmed-up step inside cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)")
     args = ap.parse_args()

@@ -114,6 +114,11 @@ CASES = {
     # the sample counts the benchmarks run (BASELINE.json configs[1..3]): every 32-sample round of the per-ray kernels
     # (transmittance carried across rounds) and both ends of their size limits meet the reference.  Small volumes and
     # few rays: the sample axis is the point.
+    # semantic branch (§8f-4): 131 -> 128 -> 24 semantic decoder, rendered feature, contrastive loss vs per-ray embeddings
+    "indoor_train_semantic": dict(
+        kind="indoor", training=True, R=24, S0=24, Si=8, vol=(128, 6, 10, 12), seed=31, semantic=24),
+    "indoor_eval_semantic": dict(
+        kind="indoor", training=False, R=12, S0=16, Si=8, vol=(128, 5, 7, 9), seed=32, semantic=24),
     "indoor_train_c2": dict(      # C2 / C3: 96 coarse + 32 importance samples
         kind="indoor", training=True, R=14, S0=96, Si=32, vol=(128, 4, 6, 8), seed=21),
     "indoor_eval_c2": dict(
@@ -125,7 +130,7 @@ CASES = {
 }
 
 
-def renderer_cfg(kind: str, S0: int, Si: int, Dict):
+def renderer_cfg(kind: str, S0: int, Si: int, Dict, semantic: int = 0):
     if kind == "indoor":
         field = dict(
             type="SDFField",
@@ -148,9 +153,41 @@ def renderer_cfg(kind: str, S0: int, Si: int, Dict):
         loss = Dict(sensor_depth_truncation=0.05, temperature=0.01,
                     weights=Dict(eikonal_loss=0.01, free_space_loss=1.0, sdf_loss=10.0, depth_loss=1.0, rgb_loss=0.0,
                                  semantic_loss=0.0))
+    if semantic:   # configs/scannet/pretrain-ponder-spunet-v1m1-0-base.py:51-57 with a small embedding width
+        field["semantic_decoder"] = dict(in_dim=131, out_dim=semantic, hidden_size=128, n_blocks=0, points_factor=0.0)
+        loss.weights.semantic_loss = 0.1
+        loss.val_ray_split = 5
     sampler = dict(type="NeuSSampler", initial_sampler="UniformSampler", num_samples=S0, num_samples_importance=Si,
                    num_upsample_steps=1, train_stratified=True, single_jitter=False)
     return dict(type="NeuSModel", field=field, collider=collider, sampler=sampler, loss=loss)
+
+
+def _gen_eval_semantic_patch(bsm, model) -> None:
+    """Run the reference's validation-mode semantic loss with `chunk_idx` defined: the reference function is executed
+    unmodified, once per chunk, on that chunk's rays (in training mode, whose branch is the same formula without the
+    broken index), and the per-chunk losses are averaged as its loop does."""
+    orig = type(model).get_loss
+
+    def get_loss(self, preds, targets):
+        chunk = self.loss.get("val_ray_split", 128)
+        w = self.loss.weights.semantic_loss
+        self.loss.weights.semantic_loss = 0.0
+        out = orig(self, preds, targets)
+        self.loss.weights.semantic_loss = w
+        R = preds["depth"].shape[0]
+        parts = []
+        was = self.training
+        self.training = True
+        for c0 in range(0, R, chunk):
+            sl = slice(c0, c0 + chunk)
+            p = {k: (v[sl] if torch.is_tensor(v) and v.shape[:1] == (R,) else v) for k, v in preds.items()}
+            t = {k: v[sl] for k, v in targets.items()}
+            parts.append(orig(self, p, t)["semantic_loss"].reshape(()) / w)
+        self.training = was
+        out["semantic_loss"] = torch.stack(parts).mean() * w
+        return out
+
+    model.get_loss = get_loss.__get__(model)
 
 
 def gen_render_case(name: str, spec: dict, Dict) -> None:
@@ -158,7 +195,8 @@ def gen_render_case(name: str, spec: dict, Dict) -> None:
 
     torch.manual_seed(spec["seed"])
     g = torch.Generator().manual_seed(spec["seed"])
-    model = build_renderer(renderer_cfg(spec["kind"], spec["S0"], spec["Si"], Dict))
+    nsem = spec.get("semantic", 0)
+    model = build_renderer(renderer_cfg(spec["kind"], spec["S0"], spec["Si"], Dict, nsem))
     model.train(spec["training"])
     R, S0, Si = spec["R"], spec["S0"], spec["Si"]
     C, Z, Y, X = spec["vol"]
@@ -181,11 +219,21 @@ def gen_render_case(name: str, spec: dict, Dict) -> None:
     with _NoiseQueue(queue):
         out = model(RayBundle(origins=o.clone(), directions=d.clone()), [volume])
     targets = {"depth": depth_gt, "rgb": rgb_gt}
+    if nsem:
+        sem_gt = torch.nn.functional.normalize(torch.randn(R, nsem, generator=g), dim=-1)
+        sem_gt[3] = 0.0; sem_gt[7] = 0.0            # pixels without a class (semantic_map stays zero, :589-597)
+        targets["semantic"] = sem_gt
+        if not spec["training"]:
+            # the reference's validation branch reads an undefined `chunk_idx` (base_surface_model.py:161); the fixture
+            # is generated with the loop's evident meaning: chunk c covers rays [c * chunk, (c + 1) * chunk)
+            import ponder.models.ponder.render_utils.models.base_surface_model as bsm
+            _gen_eval_semantic_patch(bsm, model)
     loss_dict = model.get_loss(out, targets)
     total = sum(v for k, v in loss_dict.items() if "loss" in k)
     total.backward()
 
     arrays = {
+        **({"semantic_gt": targets["semantic"]} if nsem else {}),
         "rays_o": o, "rays_d": d, "volume": volume.detach(), "depth_gt": depth_gt, "rgb_gt": rgb_gt,
         "noise_uniform": noise_u, "noise_pdf": noise_p, "total_loss": total.detach(),
         "grad_volume": volume.grad,
@@ -199,7 +247,7 @@ def gen_render_case(name: str, spec: dict, Dict) -> None:
     for k, p in model.named_parameters():
         if p.grad is not None:
             arrays["grad." + k] = p.grad
-    meta = dict(kind=spec["kind"], training=spec["training"], R=R, S0=S0, Si=Si)
+    meta = dict(kind=spec["kind"], training=spec["training"], R=R, S0=S0, Si=Si, semantic=nsem)
     np.savez_compressed(GOLD / f"render_{name}.npz", meta=json.dumps(meta),
                         **{k: v.numpy() for k, v in arrays.items()})
     print(f"render_{name}: total loss {float(total):.6f}, {len(arrays)} arrays")
@@ -289,13 +337,17 @@ def gen_rayprep_case() -> None:
             extrinsic[b, v, :3, 3] = torch.randn(3, generator=g) * 0.5 + torch.tensor([0.0, 0.0, 2.0])
             extrinsic[b, v, 3, 3] = 1.0
     depth_scale = torch.tensor([1.0, 0.5])
+    # semantic branch (§8f-4): class ids per pixel (0 = unlabelled) and a [7, 10] table of unit "text embeddings"
+    semantic = torch.randint(0, 7, (B, V, H, W), generator=g)
+    table = torch.nn.functional.normalize(torch.randn(7, 10, generator=g), dim=-1)
     dd = dict(coord=coord.clone(), offset=offset.clone(), rgb=rgb.clone(), depth=depth.clone(), intrinsic=intrinsic.clone(),
-              extrinsic=extrinsic.clone(), depth_scale=depth_scale.clone())
+              extrinsic=extrinsic.clone(), depth_scale=depth_scale.clone(), semantic=semantic.clone())
     me = object.__new__(PonderIndoor)
     padding = 0.1
     object.__setattr__(me, "bounds", np.array([[-0.5 - padding / 2] * 3, [0.5 + padding / 2] * 3], dtype=np.float32))
     object.__setattr__(me, "ray_nsample", n)
-    object.__setattr__(me, "render_semantic", False)
+    object.__setattr__(me, "render_semantic", True)
+    object.__setattr__(me, "class_embedding", table)
     object.__setattr__(me, "grid_size", 0.02)
     perms = []
     orig = torch.randperm
@@ -324,6 +376,7 @@ def gen_rayprep_case() -> None:
               "cube.coord": d1["coord"], "cube.extrinsic": d1["extrinsic"], "cube.depth_scale": d1["depth_scale"],
               "cube.pc_scale": d1["pc_scale"], "cube.bbox": d1["bbox"],
               "grid.bbox": d2["bbox"], "grid.resolution": d2["resolution"],
+              "in.semantic": semantic, "index2semantic": table, "ray.semantic": ray["semantic"],
               "ray.ray_o": ray["ray_o"], "ray.ray_d": ray["ray_d"], "ray.rgb": ray["rgb"], "ray.depth": ray["depth"]}
     np.savez_compressed(GOLD / "rayprep_indoor.npz", meta=json.dumps(dict(B=B, V=V, H=H, W=W, n=n, padding=padding,
                                                                             grid_size=0.02)),

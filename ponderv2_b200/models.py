@@ -12,7 +12,8 @@ Same constructor arguments (config dicts with `type` keys built through the regi
 dict(loss=..., <name>_loss=...)` contract on the collate dict the reference's dataloader produces, same parameter names.
 `install_into_reference()` registers these classes in the reference's own registries (force=True) and aliases
 `spconv.pytorch` / `smooth_sampler`, after which the reference's configs and `ponder/engines` run unchanged on this
-library.  The CLIP semantic branch (`render_semantic=True`, §8f-4) is not implemented and raises.
+library.  The semantic branch (`render_semantic=True`, §8f-4) takes the class text embeddings as a
+tensor / file (`class_embedding=`) or computes them with CLIP when that package is importable.
 """
 from __future__ import annotations
 
@@ -155,6 +156,53 @@ def _build_projection(cfg: Optional[dict], default: dict) -> nn.Module:
     return MODELS.build(dict(cfg) if cfg is not None else default).to(memory_format=torch.channels_last_3d)
 
 
+def _class_embedding(given, template, clip_model, class_name) -> torch.Tensor:
+    """[n_classes, E] unit-norm text embeddings of the class prompts.  `PonderIndoor.load_semantic` (:85-118) computes
+    them with CLIP at construction; here they are either handed in (`class_embedding=` tensor / array / .npy / .pt path,
+    e.g. saved once from the reference) or computed the same way when the `clip` package and weights are available."""
+    if given is not None:
+        if isinstance(given, (str, bytes)):
+            import numpy as np
+            given = torch.load(given) if str(given).endswith((".pt", ".pth")) else torch.from_numpy(np.load(given))
+        emb = torch.as_tensor(given).float()
+        return emb / emb.norm(dim=-1, keepdim=True).clamp(min=1e-12)
+    try:
+        import clip                                                     # noqa: F401
+    except ImportError as e:
+        raise RuntimeError("PonderIndoor-v2(render_semantic=True): pass class_embedding=<[n_classes, E] text embeddings> "
+                           "(CLIP is not importable here to compute them from template / class_name)") from e
+    model, _ = clip.load(clip_model, device="cpu", download_root="./.cache/clip")
+    multi = not isinstance(template, str)
+    prompts = [t.replace("[x]", n) for n in class_name for t in (template if multi else [template])]
+    with torch.no_grad():
+        emb = model.encode_text(clip.tokenize(prompts)).float()
+    emb = emb / emb.norm(dim=-1, keepdim=True)
+    if multi:
+        emb = emb.reshape(len(class_name), len(template), -1).mean(1)
+        emb = emb / emb.norm(dim=-1, keepdim=True)
+    return emb
+
+
+class _Criteria(nn.Module):
+    """`build_criteria` (ponder/models/losses/builder.py) for the PPT point loss: a list of weighted criteria; the
+    shipped PPT configs use CrossEntropyLoss(loss_weight, ignore_index)."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        self.items = []
+        for c in (cfg if isinstance(cfg, (list, tuple)) else [cfg]):
+            c = dict(c)
+            t = c.pop("type")
+            if t != "CrossEntropyLoss":
+                raise NotImplementedError(f"ppt_criteria {t}: only CrossEntropyLoss is wired")
+            self.items.append((float(c.get("loss_weight", 1.0)), int(c.get("ignore_index", -1)),
+                               float(c.get("label_smoothing", 0.0))))
+
+    def forward(self, logits, target):
+        return sum(w * F.cross_entropy(logits, target.long(), ignore_index=ig, label_smoothing=ls)
+                   for w, ig, ls in self.items)
+
+
 class PonderIndoor(PonderIndoorStep):
     """`PonderIndoor` with the reference's constructor and data_dict contract (ponder_indoor_base.py:19-706): takes the
     collate dict (coord, grid_coord, feat, offset, rgb (B,V,H,W,3), depth (B,V,H,W), intrinsic, extrinsic (B,V,4,4),
@@ -163,10 +211,7 @@ class PonderIndoor(PonderIndoorStep):
     def __init__(self, backbone, projection, renderer, mask=None, grid_shape=64, grid_size=0.02, val_ray_split=10240,
                  ray_nsample=128, padding=0.1, backbone_out_channels=96, context_channels=256, pool_type="mean",
                  render_semantic=False, conditions=None, template=None, clip_model=None, class_name=None,
-                 valid_index=None, ppt_loss_weight=1.0, ppt_criteria=None):
-        if render_semantic:
-            raise NotImplementedError("PonderIndoor-v2: render_semantic=True needs CLIP text embeddings (SURVEY §8f-4); "
-                                      "set render_semantic=False and loss.weights.semantic_loss=0")
+                 valid_index=None, ppt_loss_weight=1.0, ppt_criteria=None, class_embedding=None, logit_scale=4.6052):
         gs = tuple(grid_shape) if isinstance(grid_shape, Sequence) else (grid_shape,) * 3
         nn.Module.__init__(self)
         if pool_type != "mean":
@@ -187,6 +232,19 @@ class PonderIndoor(PonderIndoorStep):
         self.conditions = tuple(conditions) if conditions is not None else None
         if self.conditions is not None:   # PPT context table (:66; consumed by the PDNorm backbones, §8f-3)
             self.embedding_table = nn.Embedding(len(self.conditions), context_channels)
+        # semantic branch (§8f-4, :73-118): per-class text embeddings, rendered-feature contrastive loss, PPT point loss
+        self.render_semantic = bool(render_semantic)
+        self.valid_index = valid_index
+        self.ppt_loss_weight = float(ppt_loss_weight) if render_semantic else 0.0
+        if self.render_semantic:
+            emb = _class_embedding(class_embedding, template, clip_model, class_name)
+            self.register_buffer("class_embedding", emb)
+            self.logit_scale = nn.Parameter(torch.tensor(float(logit_scale)), requires_grad=False)   # CLIP's, frozen
+            if self.ppt_loss_weight > 0:
+                if ppt_criteria is None:
+                    raise ValueError("PonderIndoor-v2: ppt_loss_weight > 0 needs ppt_criteria (ponder_indoor_base.py:81)")
+                self.ppt_criteria = _Criteria(ppt_criteria)
+                self.proj_head = nn.Linear(backbone_out_channels, emb.shape[1])
 
     mask_features = PonderOutdoorStep.mask_features      # the same block masking (:121-161)
 
@@ -201,11 +259,29 @@ class PonderIndoor(PonderIndoorStep):
             data_dict["context"] = self.embedding_table.weight[idx:idx + 1]
         data_dict["sparse_backbone_feat"] = self.backbone(data_dict)                     # extract_feature
         cube = rayprep.to_unit_cube(data_dict)                                           # prepare_ray
+        if self.render_semantic:
+            cube["index2semantic"] = self._class_table(data_dict)
         ray = rayprep.ray_sample(cube, self.ray_nsample, self.bounds, pixels=noise.get("pixels"))
         cube = rayprep.grid_sample(cube, self.grid_size)                                 # prepare_volume
         cube["sparse_backbone_feat"] = data_dict["sparse_backbone_feat"]
         cube.update(ray_o=ray["ray_o"], ray_d=ray["ray_d"], rgb=ray["rgb"], depth=ray["depth"])
-        return self.forward_after_backbone(cube, noise)
+        cube.pop("semantic", None)                          # the (B,V,H,W) class-id maps; rays carry embeddings
+        if "semantic" in ray:
+            cube["semantic"] = ray["semantic"]
+        out = self.forward_after_backbone(cube, noise)
+        if self.ppt_loss_weight > 0:                                                     # ppt_loss (:680-691)
+            feat = F.normalize(self.proj_head(data_dict["sparse_backbone_feat"].float()), dim=-1)
+            logits = self.logit_scale.exp() * (feat @ self._class_table(data_dict).t())
+            out["ppt_loss"] = self.ppt_criteria(logits, data_dict["segment"])
+        return out
+
+    def _class_table(self, data_dict) -> torch.Tensor:
+        """Rows of `class_embedding` valid for the batch's condition (:514-523)."""
+        if "condition" in data_dict and self.valid_index is not None and self.conditions is not None:
+            idx = torch.as_tensor(self.valid_index[self.conditions.index(data_dict["condition"][0])],
+                                  device=self.class_embedding.device)
+            return self.class_embedding[idx]
+        return self.class_embedding
 
 
 class PonderOutdoor(PonderOutdoorStep):

@@ -131,7 +131,10 @@ class PonderIndoorStep(nn.Module):
                          for oo, dd in zip(o.split(self.val_ray_split), d.split(self.val_ray_split))]
                 outs.append({k: torch.cat([q[k].detach() for q in parts], 0) for k in parts[0]})
         render_out = outs[0] if len(outs) == 1 else {k: torch.cat([o[k] for o in outs], dim=0) for k in outs[0]}
-        loss_dict = self.renderer.get_loss(render_out, {"depth": data_dict["depth"], "rgb": data_dict.get("rgb")})
+        targets = {"depth": data_dict["depth"], "rgb": data_dict.get("rgb")}
+        if "semantic" in data_dict and data_dict["semantic"].is_floating_point():   # per-ray text embeddings (§8f-4)
+            targets["semantic"] = data_dict["semantic"]
+        loss_dict = self.renderer.get_loss(render_out, targets)
         loss = sum(v for k, v in loss_dict.items() if "loss" in k)
         return dict(loss=loss, **loss_dict)
 

@@ -88,7 +88,8 @@ def sample_pixels(depth: torch.Tensor, n: int, keys: Optional[torch.Tensor] = No
 @torch.no_grad()
 def ray_sample(data_dict: Dict[str, torch.Tensor], ray_nsample: int, bounds: Sequence[Sequence[float]],
                pixels: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
-    """ponder_indoor_base.py:446-620 (semantic branch: SURVEY §8f-4).  `data_dict` after `to_unit_cube`.
+    """ponder_indoor_base.py:446-620.  `data_dict` after `to_unit_cube`; with `semantic` (B,V,H,W class ids) and
+    `index2semantic` ([K, E] text embeddings) in it, the per-ray embedding target of the semantic branch (§8f-4) is added.
     pixels: optional [B,V,n] flat pixel indices (tests inject the reference's choice).
     -> ray_o, ray_d [B, V*n, 3]; rgb [B*V*n, 3]; depth [B*V*n, 1] (point-to-point, -0.001 where the ray misses the box)."""
     rgb = data_dict["rgb"].float()
@@ -134,5 +135,14 @@ def ray_sample(data_dict: Dict[str, torch.Tensor], ray_nsample: int, bounds: Seq
     hit = near < far
     color = torch.where(hit[..., None], color, torch.zeros_like(color))
     d = torch.where(hit, d, torch.full_like(d, -0.001))
-    return dict(ray_o=ray_o.reshape(B, V * n, 3).contiguous(), ray_d=ray_d.reshape(B, V * n, 3).contiguous(),
-                rgb=color.reshape(-1, color.shape[-1]).contiguous(), depth=d.reshape(-1, 1).contiguous())
+    out = dict(ray_o=ray_o.reshape(B, V * n, 3).contiguous(), ray_d=ray_d.reshape(B, V * n, 3).contiguous(),
+               rgb=color.reshape(-1, color.shape[-1]).contiguous(), depth=d.reshape(-1, 1).contiguous())
+    if "semantic" in data_dict and "index2semantic" in data_dict:
+        # :581-597: class id of the sampled pixel (-1 outside the box), looked up in the text-embedding table; ids <= 0
+        # (unlabelled / ignored) keep an all-zero target, which the loss masks out
+        table = data_dict["index2semantic"].float()
+        ids = torch.gather(data_dict["semantic"].reshape(B, V, H * W).long(), 2, pixels)
+        ids = torch.where(hit.expand_as(ids), ids, torch.full_like(ids, -1))
+        emb = table[ids.clamp(min=0, max=table.shape[0] - 1)] * (ids > 0)[..., None].float()
+        out["semantic"] = emb.reshape(-1, table.shape[-1]).contiguous()
+    return out

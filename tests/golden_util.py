@@ -52,5 +52,10 @@ def product_renderer_cfg(meta):
     sampler = dict(type="NeuSSampler", initial_sampler="UniformSampler", num_samples=meta["S0"],
                    num_samples_importance=meta["Si"], num_upsample_steps=1, train_stratified=True,
                    single_jitter=False)
-    return dict(type="NeuSModel", field=field, collider=collider, sampler=sampler,
-                loss=dict(sensor_depth_truncation=0.05, temperature=0.01, weights=weights))
+    loss = dict(sensor_depth_truncation=0.05, temperature=0.01, weights=weights)
+    if meta.get("semantic"):   # §8f-4 fixtures (oracle/gen_golden.py:renderer_cfg)
+        field["semantic_decoder"] = dict(in_dim=131, out_dim=meta["semantic"], hidden_size=128, n_blocks=0,
+                                         points_factor=0.0)
+        weights["semantic_loss"] = 0.1
+        loss["val_ray_split"] = 5
+    return dict(type="NeuSModel", field=field, collider=collider, sampler=sampler, loss=loss)

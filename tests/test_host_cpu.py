@@ -107,8 +107,10 @@ def test_rayprep_matches_reference_golden():
         assert (cube[k] - ref).abs().max().item() < 2e-5 * max(1.0, ref.abs().max().item()), k
     pad = meta["padding"]
     bounds = [[-0.5 - pad / 2] * 3, [0.5 + pad / 2] * 3]
+    cube["index2semantic"] = t["index2semantic"]          # semantic branch (§8f-4): class ids -> text embeddings
     ray = rayprep.ray_sample(cube, meta["n"], bounds, pixels=t["pixels"])
-    for k in ("ray_o", "ray_d", "rgb", "depth"):
+    assert float(t["ray.semantic"].abs().sum()) > 0
+    for k in ("ray_o", "ray_d", "rgb", "depth", "semantic"):
         ref = t["ray." + k]
         assert ray[k].shape == ref.shape, (k, ray[k].shape, ref.shape)
         assert (ray[k] - ref).abs().max().item() < 5e-5 * max(1.0, ref.abs().max().item()), k
@@ -300,3 +302,23 @@ def test_spunet_v1m3_state_dict_contract():
     assert got == want
     # zero_init: the modulation starts as the identity
     assert all(float(p.abs().max()) == 0.0 for k, p in m.named_parameters() if "modulation" in k)
+
+
+def test_semantic_loss_matches_reference_golden():
+    """NeuSModel._semantic_loss (§8f-4: sync-free masked contrastive cross entropy; eval = mean over val_ray_split
+    chunks) on the reference's own rendered features against the reference's loss value (base_surface_model.py:123-173,
+    tests/golden/render_indoor_{train,eval}_semantic.npz)."""
+    from ponderv2_b200.render import build_renderer
+    from tests.golden_util import load_render_case, product_renderer_cfg
+    for case in ("indoor_train_semantic", "indoor_eval_semantic"):
+        meta, arr, sd, _ = load_render_case(case)
+        m = build_renderer(product_renderer_cfg(meta))
+        m.load_state_dict(sd, strict=True)
+        m.train(meta["training"])
+        got = m._semantic_loss({"semantic": arr["out.semantic"]}, {"semantic": arr["semantic_gt"], "depth": arr["depth_gt"]})
+        ref = float(arr["loss.semantic_loss"])
+        assert abs(float(got) * 0.1 - ref) < 1e-5 * max(1.0, abs(ref)), (case, float(got) * 0.1, ref)
+    # all rays ignored -> exactly 0 (the reference's explicit branch), no NaN
+    z = m._semantic_loss({"semantic": arr["out.semantic"]},
+                         {"semantic": torch.zeros_like(arr["semantic_gt"]), "depth": arr["depth_gt"]})
+    assert float(z) == 0.0
