@@ -565,12 +565,13 @@ struct PersistLayout {
   int meta_bytes;   // one metadata buffer: idx[kvol][128] | row[128] | active[num_chunks] | n_active
   int fixed;        // everything except the stage ring
 };
-__host__ __device__ inline PersistLayout persist_layout(int kvol, int num_chunks) {
+__host__ __device__ inline PersistLayout persist_layout(int kvol, int num_chunks, int nbuf = 2) {
   PersistLayout L;
   L.meta_bytes = (kvol * kTileM * 4 + kTileM * 4 + num_chunks * 2 + 16 + 15) / 16 * 16;
-  L.fixed = 2 * L.meta_bytes + num_chunks * 32 /*kc table*/ + 32 * 8 /*barriers*/ + 64 + 1024 /*alignment*/;
+  L.fixed = nbuf * L.meta_bytes + num_chunks * 32 /*kc table*/ + 32 * 8 /*barriers*/ + 64 + 1024 /*alignment*/;
   return L;
 }
+constexpr int kMetaBufs = 3;   // metadata buffers of the fp32 persistent kernel (prepared two tiles ahead)
 
 __device__ __forceinline__ void bar_sync_named(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -600,9 +601,14 @@ __device__ __forceinline__ void split_store_bf16(uint32_t addr, uint32_t lo_delt
 //   truncating fp32 accumulation (~ n_steps * 2^-24).  The weight operand is pre-split once per call into bf16 hi / lo
 //   matrices [Cout][K * Cin] and arrives by TMA (one 2-D box of n_pad rows x 128 B per half and chunk, hardware swizzle),
 //   so the producer warps only gather activations.
-template <bool kBx3>
-__global__ void __launch_bounds__(kPersistThreads) umma_gather_gemm_persistent_kernel(const GGParams p, int num_tiles,
-                                                                                      const __grid_constant__ CUtensorMap wmap) {
+// kG = producer groups (128 threads each; a group has one chunk in flight).  More groups did not help (r2p): the gathers
+// were not the critical path, the metadata preparation was (see the epilogue group below).
+template <bool kBx3, int kG = 2>
+__global__ void __launch_bounds__((kG * 4 + 5) * 32) umma_gather_gemm_persistent_kernel(const GGParams p, int num_tiles,
+                                                                                        const __grid_constant__ CUtensorMap wmap) {
+  constexpr int kPersistGroups = kG;
+  constexpr int kPersistProducerWarps = kG * 4;
+  constexpr int kPersistThreads = (kG * 4 + 5) * 32;   // producers | MMA warp | 4 epilogue warps
   constexpr int kEPR = kBx3 ? 64 : 32;   // contraction elements per 128-byte operand row (chunk)
   constexpr int kEPP = kBx3 ? 8 : 4;     // ... per 16-byte piece
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -610,16 +616,16 @@ __global__ void __launch_bounds__(kPersistThreads) umma_gather_gemm_persistent_k
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b_bytes = p.n_pad * 128;
   const int stage_bytes = (kABytes + b_bytes) * 2;
-  const PersistLayout L = persist_layout(p.kvol, p.num_chunks);
+  const PersistLayout L = persist_layout(p.kvol, p.num_chunks, kMetaBufs);
   uint8_t* stage_base = smem;
   uint8_t* meta_base = smem + (size_t)p.stages * stage_bytes;
-  uint32_t* kc_s = reinterpret_cast<uint32_t*>(meta_base + 2 * L.meta_bytes);
+  uint32_t* kc_s = reinterpret_cast<uint32_t*>(meta_base + kMetaBufs * L.meta_bytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(kc_s + p.num_chunks * 8);
   uint64_t* full_bar = bars;                        // [kMaxStages]  128 arrivals (the producing group)
   uint64_t* empty_bar = bars + kMaxStages;          // [kMaxStages]  tcgen05.commit
-  uint64_t* meta_full = bars + 2 * kMaxStages;      // [2]           1 arrival (epilogue group leader)
-  uint64_t* meta_empty = meta_full + 2;             // [2]           producer warps + MMA warp
-  uint64_t* tmem_full = meta_empty + 2;             // [2]           tcgen05.commit / plain arrive for empty tiles
+  uint64_t* meta_full = bars + 2 * kMaxStages;      // [kMetaBufs]   1 arrival (epilogue group leader)
+  uint64_t* meta_empty = meta_full + kMetaBufs;     // [kMetaBufs]   producer warps + MMA warp
+  uint64_t* tmem_full = meta_empty + kMetaBufs;     // [2]           tcgen05.commit / plain arrive for empty tiles
   uint64_t* tmem_empty = tmem_full + 2;             // [2]           4 epilogue warps
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   uint32_t* scratch = tmem_slot + 1;                // [16] epilogue-group scratch (kmask[4], warp counts[4], total)
@@ -635,9 +641,11 @@ __global__ void __launch_bounds__(kPersistThreads) umma_gather_gemm_persistent_k
 
   if (tid == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(smem_u32(&full_bar[s]), 128); mbar_init(smem_u32(&empty_bar[s]), 1); }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < kMetaBufs; ++b) {
       mbar_init(smem_u32(&meta_full[b]), 1);
       mbar_init(smem_u32(&meta_empty[b]), kPersistProducerWarps + 1);
+    }
+    for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(&tmem_full[b]), 1);
       mbar_init(smem_u32(&tmem_empty[b]), 4);
     }
@@ -674,8 +682,8 @@ __global__ void __launch_bounds__(kPersistThreads) umma_gather_gemm_persistent_k
     const uint64_t wstep = 16ull * p.w_sco32;
     int gbase = 0;   // global chunk counter at the start of the tile (same in every thread)
     for (int i = 0; i < my_tiles; ++i) {
-      const int b = i & 1;
-      mbar_wait(smem_u32(&meta_full[b]), (uint32_t)(i >> 1) & 1u);
+      const int b = i % kMetaBufs;
+      mbar_wait(smem_u32(&meta_full[b]), (uint32_t)(i / kMetaBufs) & 1u);
       const int n_active = *meta_count(b);
       const int32_t* idx_s = meta_idx(b);
       const uint16_t* active = meta_active(b);
@@ -760,9 +768,9 @@ __global__ void __launch_bounds__(kPersistThreads) umma_gather_gemm_persistent_k
     const uint32_t idesc = make_idesc(kBx3 ? 1 : 2, kTileM, p.n_pad);
     int gbase = 0;
     for (int i = 0; i < my_tiles; ++i) {
-      const int b = i & 1;
-      mbar_wait(smem_u32(&meta_full[b]), (uint32_t)(i >> 1) & 1u);
-      const int n_active = *meta_count(b);
+      const int b = i & 1, mb = i % kMetaBufs;
+      mbar_wait(smem_u32(&meta_full[mb]), (uint32_t)(i / kMetaBufs) & 1u);
+      const int n_active = *meta_count(mb);
       mbar_wait(smem_u32(&tmem_empty[b]), ((uint32_t)(i >> 1) & 1u) ^ 1u);   // accumulator b drained (first two: free)
       tc_fence_after();
       const uint32_t acc = tmem_base + (uint32_t)b * acc_stride;
@@ -796,7 +804,7 @@ __global__ void __launch_bounds__(kPersistThreads) umma_gather_gemm_persistent_k
       if (n_active == 0 && lane == 0) mbar_arrive(smem_u32(&tmem_full[b]));   // nothing to accumulate: epilogue writes bias only
       gbase += n_active;
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&meta_empty[b]));
+      if (lane == 0) mbar_arrive(smem_u32(&meta_empty[mb]));
     }
     tc_fence_before();
   } else {
@@ -804,24 +812,41 @@ __global__ void __launch_bounds__(kPersistThreads) umma_gather_gemm_persistent_k
     const int ew = warp - kPersistProducerWarps - 1;   // 0..3: index within the epilogue group
     const int lg = warp & 3;                           // TMEM lane group this warp may read (hardware: warp id % 4)
     const int et = tid - (kPersistProducerWarps + 1) * 32;   // 0..127
-    auto prepare = [&](int j) {
-      const int b = j & 1;
-      mbar_wait(smem_u32(&meta_empty[b]), ((uint32_t)(j >> 1) & 1u) ^ 1u);
+    // Metadata is prepared TWO tiles ahead in two halves: `issue(j)` puts the tile's global loads (row order + up to 27
+    // neighbour indices per row) in flight into registers, the accumulator drain of the current tile runs under their
+    // latency, and `finish(j)` stores them and compacts the active-chunk list.  (ncu, profiles/r2q_gg32: with the whole
+    // preparation done back to back before each drain, producers and the MMA warp spent 18 % of all warp samples
+    // waiting for the next tile's metadata - the epilogue group was the critical path of the kernel.)
+    constexpr int kRegIdx = 27;
+    int32_t pre_row = -1;
+    int32_t pre_idx[kRegIdx];
+    auto issue = [&](int j) {
+      const int64_t pos = tile_row0(j) + et;
+      const bool in = pos < p.n_out;
+      pre_row = -1;
+      if (in) pre_row = (p.order != nullptr) ? __ldg(&p.order[pos]) : (int32_t)pos;
+#pragma unroll
+      for (int u = 0; u < kRegIdx; ++u) {
+        pre_idx[u] = -1;
+        if (u < p.kvol && in) pre_idx[u] = (p.nbr != nullptr) ? __ldg(&p.nbr[(int64_t)u * p.n_out + pos]) : (int32_t)pos;
+      }
+    };
+    auto finish = [&](int j) {
+      const int b = j % kMetaBufs;
+      mbar_wait(smem_u32(&meta_empty[b]), ((uint32_t)(j / kMetaBufs) & 1u) ^ 1u);
       int32_t* idx_s = meta_idx(b);
       int32_t* row_s = meta_row(b);
       uint16_t* active = meta_active(b);
       const int64_t row0 = tile_row0(j);
-      {
-        const int64_t pos = row0 + et;
-        int32_t jr = -1;
-        if (pos < p.n_out) jr = (p.order != nullptr) ? __ldg(&p.order[pos]) : (int32_t)pos;
-        row_s[et] = jr;
-      }
+      row_s[et] = pre_row;
       if (et < 4) scratch[et] = 0u;   // kmask
-      // neighbour indices: thread et owns row et of the tile for every offset; batches of 9 loads
+#pragma unroll
+      for (int u = 0; u < kRegIdx; ++u)
+        if (u < p.kvol) idx_s[u * kTileM + et] = pre_idx[u];
+      // kernels with more than 27 offsets (the 5^3 stem): the rest in batches of 9 loads
       const int64_t pos = row0 + et;
       const bool in = pos < p.n_out;
-      for (int k0 = 0; k0 < p.kvol; k0 += 9) {
+      for (int k0 = kRegIdx; k0 < p.kvol; k0 += 9) {
         int32_t v[9];
 #pragma unroll
         for (int u = 0; u < 9; ++u) {
@@ -866,14 +891,16 @@ __global__ void __launch_bounds__(kPersistThreads) umma_gather_gemm_persistent_k
       bar_sync_named(1, 128);   // every epilogue thread's metadata writes are done
       if (et == 0) mbar_arrive(smem_u32(&meta_full[b]));
     };
-    if (my_tiles > 0) prepare(0);
+    if (my_tiles > 0) { issue(0); finish(0); }
+    if (my_tiles > 1) { issue(1); finish(1); }
     for (int i = 0; i < my_tiles; ++i) {
-      if (i + 1 < my_tiles) prepare(i + 1);
-      const int b = i & 1;
+      const bool ahead = i + 2 < my_tiles;
+      if (ahead) issue(i + 2);
+      const int b = i & 1, mb = i % kMetaBufs;
       mbar_wait(smem_u32(&tmem_full[b]), (uint32_t)(i >> 1) & 1u);
       tc_fence_after();
-      const int n_active = *meta_count(b);
-      const int32_t j32 = meta_row(b)[lg * 32 + lane];
+      const int n_active = *meta_count(mb);
+      const int32_t j32 = meta_row(mb)[lg * 32 + lane];
       const int64_t j = j32;
       const uint32_t acc = tmem_base + (uint32_t)b * acc_stride + ((uint32_t)(lg * 32) << 16);
       for (int col0 = 0; col0 < p.n_pad; col0 += 16) {
@@ -897,6 +924,7 @@ __global__ void __launch_bounds__(kPersistThreads) umma_gather_gemm_persistent_k
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&tmem_empty[b]));   // accumulator b may be overwritten
+      if (ahead) finish(i + 2);
     }
   }
   __syncthreads();
@@ -1232,10 +1260,13 @@ int launch_persistent(const GGParams& p0, cudaStream_t stream, const void* w2 = 
   while ((int)p.tmem_cols < 2 * p.n_pad) p.tmem_cols <<= 1;     // two accumulators
   if (p.tmem_cols > 512) return PV2_EUNSUPPORTED;
   const int stage_bytes = (kABytes + p.n_pad * 128) * 2;
-  const PersistLayout L = persist_layout(p.kvol, p.num_chunks);
+  const PersistLayout L = persist_layout(p.kvol, p.num_chunks, kMetaBufs);
   int stages = (227 * 1024 - L.fixed) / stage_bytes;   // 227 KB: the opt-in maximum of dynamic shared memory per CTA
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < kPersistGroups) return PV2_EUNSUPPORTED;          // groups <= stages (mbarrier parity aliasing)
+  int groups = pv2_get_option("gg_groups");
+  if (groups < 2 || groups > 4) groups = 2;   // measured (profiles/r2p_micro_levels_g{2,3,4}.txt): no difference
+  if (!bx3 || stages < groups + 1) groups = 2;
   p.stages = stages;
   p.ksplit = 1;
   p.ablate = 0;
@@ -1244,17 +1275,28 @@ int launch_persistent(const GGParams& p0, cudaStream_t stream, const void* w2 = 
   CUtensorMap wmap;
   memset(&wmap, 0, sizeof(wmap));
   if (bx3) {
-    static bool done[64] = {};
-    cudaError_t e = ensure_smem_optin(umma_gather_gemm_persistent_kernel<true>, done);
-    if (e != cudaSuccess) return (int)e;
     const int rc = encode_bf16_map(&wmap, w2, 2 * (int64_t)p.w2_rows, w2_cols, p.n_pad);
     if (rc != 0) return rc;
-    umma_gather_gemm_persistent_kernel<true><<<grid, kPersistThreads, smem, stream>>>(p, tiles, wmap);
+    static bool done2[64] = {}, done3[64] = {}, done4[64] = {};
+    cudaError_t e = cudaSuccess;
+    if (groups == 4) {
+      e = ensure_smem_optin(umma_gather_gemm_persistent_kernel<true, 4>, done4);
+      if (e != cudaSuccess) return (int)e;
+      umma_gather_gemm_persistent_kernel<true, 4><<<grid, (4 * 4 + 5) * 32, smem, stream>>>(p, tiles, wmap);
+    } else if (groups == 3) {
+      e = ensure_smem_optin(umma_gather_gemm_persistent_kernel<true, 3>, done3);
+      if (e != cudaSuccess) return (int)e;
+      umma_gather_gemm_persistent_kernel<true, 3><<<grid, (3 * 4 + 5) * 32, smem, stream>>>(p, tiles, wmap);
+    } else {
+      e = ensure_smem_optin(umma_gather_gemm_persistent_kernel<true, 2>, done2);
+      if (e != cudaSuccess) return (int)e;
+      umma_gather_gemm_persistent_kernel<true, 2><<<grid, kPersistThreads, smem, stream>>>(p, tiles, wmap);
+    }
   } else {
     static bool done[64] = {};
-    cudaError_t e = ensure_smem_optin(umma_gather_gemm_persistent_kernel<false>, done);
+    cudaError_t e = ensure_smem_optin(umma_gather_gemm_persistent_kernel<false, 2>, done);
     if (e != cudaSuccess) return (int)e;
-    umma_gather_gemm_persistent_kernel<false><<<grid, kPersistThreads, smem, stream>>>(p, tiles, wmap);
+    umma_gather_gemm_persistent_kernel<false, 2><<<grid, kPersistThreads, smem, stream>>>(p, tiles, wmap);
   }
   PV2_DONE(1);
 }
