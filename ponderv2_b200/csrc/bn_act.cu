@@ -7,6 +7,8 @@
 // backward = one reduction pass (d gamma, d beta with the ReLU mask applied on the fly) + one fused apply pass that
 // writes dx and the residual gradient.  Pure HBM-bound elementwise/reduction work: float4 accesses, per-block partial
 // sums combined in double by a one-block finalize kernel (no atomics, deterministic).
+#include <cooperative_groups.h>
+
 #include "pv2_common.cuh"
 
 namespace {
@@ -191,60 +193,109 @@ __global__ void bn_apply_bwd_kernel(const void* __restrict__ x, const void* __re
 }
 
 // ---- small batches (N <= kSmallN rows: the deep U-Net levels, 381 / 1567 voxels at C2) ---------------------------------
-// One launch instead of three: a block owns 32 channels (8 float4 groups x 32 row lanes), sums its rows, reduces through
-// shared memory in a fixed order (deterministic, double precision like the two-level path), then applies.  The second pass
-// re-reads rows that are still in L1/L2; three ~7 us launches become one.
+// One launch instead of three.  A thread-block CLUSTER of kSmallSplit CTAs owns 32 channels (8 float4 groups): each CTA
+// sums its slice of the rows (8 channel groups x 32 row lanes, double accumulation), the CTAs exchange their totals
+// through distributed shared memory in a fixed order (deterministic), every CTA derives the statistics and applies them
+// to its own rows, which are still in L1/L2.  (The first version ran one CTA per 32 channels: 8 CTAs for C = 256, 25 -
+// 35 us per launch, 1.7 ms per step in profiles/r2s_launch_summary.txt - slower than the three launches it replaced.)
 constexpr int kSmallN = 2048;
+constexpr int kSmallSplit = 8;
+
+__device__ __forceinline__ double shfl_xor_f64(double v, int m) {
+  int lo = __double2loint(v), hi = __double2hiint(v);
+  lo = __shfl_xor_sync(0xffffffffu, lo, m);
+  hi = __shfl_xor_sync(0xffffffffu, hi, m);
+  return __hiloint2double(hi, lo);
+}
+
+// Block + cluster reduction of the per-thread sums a[4], b[4] (thread = channel group tid & 7, row lane tid >> 3).
+// Returns, in threads tid < 32 (channel group tid & 7, component tid >> 3), the cluster totals of a and b.
+__device__ __forceinline__ void small_reduce(double a[4], double b[4], double (*s_w)[2][8][4], double (*s_t)[8][4],
+                                             double& tot_a, double& tot_b) {
+  namespace cgp = cooperative_groups;
+  cgp::cluster_group cluster = cgp::this_cluster();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, cgl = tid & 7;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    a[i] += shfl_xor_f64(a[i], 8);  b[i] += shfl_xor_f64(b[i], 8);
+    a[i] += shfl_xor_f64(a[i], 16); b[i] += shfl_xor_f64(b[i], 16);
+  }
+  if (lane < 8) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { s_w[warp][0][cgl][i] = a[i]; s_w[warp][1][cgl][i] = b[i]; }
+  }
+  __syncthreads();
+  if (tid < 32) {
+    const int c = tid & 7, i = tid >> 3;
+    double sa = 0.0, sb = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { sa += s_w[w][0][c][i]; sb += s_w[w][1][c][i]; }
+    s_t[0][c][i] = sa; s_t[1][c][i] = sb;
+  }
+  cluster.sync();
+  tot_a = 0.0; tot_b = 0.0;
+  if (tid < 32) {
+    const int c = tid & 7, i = tid >> 3;
+#pragma unroll
+    for (int q = 0; q < kSmallSplit; ++q) {
+      const double* remote = reinterpret_cast<const double*>(cluster.map_shared_rank(&s_t[0][0][0], q));
+      tot_a += remote[(0 * 8 + c) * 4 + i];
+      tot_b += remote[(1 * 8 + c) * 4 + i];
+    }
+  }
+}
 
 template <bool kBf16>
-__global__ void __launch_bounds__(256) bn_small_fwd_kernel(const void* __restrict__ x, const void* __restrict__ res,
-                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                           float* __restrict__ running_mean, float* __restrict__ running_var,
-                                                           float momentum, float eps, int relu, int64_t N, int C4,
-                                                           void* __restrict__ y, float* __restrict__ mean,
-                                                           float* __restrict__ invstd) {
-  __shared__ double s_a[32][8][4], s_b[32][8][4];
+__global__ void __cluster_dims__(1, kSmallSplit, 1) __launch_bounds__(256)
+bn_small_fwd_kernel(const void* __restrict__ x, const void* __restrict__ res, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, float* __restrict__ running_mean, float* __restrict__ running_var,
+                    float momentum, float eps, int relu, int64_t N, int C4, void* __restrict__ y, float* __restrict__ mean,
+                    float* __restrict__ invstd) {
+  namespace cgp = cooperative_groups;
+  __shared__ double s_w[8][2][8][4], s_t[2][8][4];
   __shared__ float s_mu[8][4], s_is[8][4];
   const int cgl = threadIdx.x & 7, rl = threadIdx.x >> 3;
   const int cg = blockIdx.x * 8 + cgl;
   const bool on = cg < C4;
+  const int64_t chunk = (N + kSmallSplit - 1) / kSmallSplit;
+  const int64_t r0 = (int64_t)blockIdx.y * chunk;
+  const int64_t r1 = (r0 + chunk < N) ? r0 + chunk : N;
   double a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
   if (on) {
-    for (int64_t r = rl; r < N; r += 32) {
+#pragma unroll 4
+    for (int64_t r = r0 + rl; r < r1; r += 32) {
       const float4 v = ld4<kBf16>(x, r * C4 + cg);
       a[0] += v.x; a[1] += v.y; a[2] += v.z; a[3] += v.w;
       b[0] += (double)v.x * v.x; b[1] += (double)v.y * v.y; b[2] += (double)v.z * v.z; b[3] += (double)v.w * v.w;
     }
   }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) { s_a[rl][cgl][i] = a[i]; s_b[rl][cgl][i] = b[i]; }
-  __syncthreads();
-  if (rl == 0 && on) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      double sa = 0.0, sb = 0.0;
-      for (int r = 0; r < 32; ++r) { sa += s_a[r][cgl][i]; sb += s_b[r][cgl][i]; }
-      const double m = sa / (double)N;
-      double var = sb / (double)N - m * m;
-      if (var < 0.0) var = 0.0;
-      const int c = cg * 4 + i;
-      const float is = (float)(1.0 / sqrt(var + (double)eps));
-      s_mu[cgl][i] = (float)m; s_is[cgl][i] = is;
-      mean[c] = (float)m; invstd[c] = is;
+  double sa, sb;
+  small_reduce(a, b, s_w, s_t, sa, sb);
+  if (threadIdx.x < 32) {
+    const int c = threadIdx.x & 7, i = threadIdx.x >> 3;
+    const int ch = (blockIdx.x * 8 + c) * 4 + i;
+    const double m = sa / (double)N;
+    double var = sb / (double)N - m * m;
+    if (var < 0.0) var = 0.0;
+    const float is = (float)(1.0 / sqrt(var + (double)eps));
+    s_mu[c][i] = (float)m; s_is[c][i] = is;
+    if (blockIdx.y == 0 && blockIdx.x * 8 + c < C4) {
+      mean[ch] = (float)m; invstd[ch] = is;
       if (running_mean != nullptr) {
         const double unb = N > 1 ? var * (double)N / (double)(N - 1) : var;
-        running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * m);
-        running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unb);
+        running_mean[ch] = (float)((1.0 - momentum) * running_mean[ch] + momentum * m);
+        running_var[ch] = (float)((1.0 - momentum) * running_var[ch] + momentum * unb);
       }
     }
   }
-  __syncthreads();
+  cgp::this_cluster().sync();   // statistics visible to the block; no CTA leaves while its totals may still be read
   if (!on) return;
   const float4 mu = make_float4(s_mu[cgl][0], s_mu[cgl][1], s_mu[cgl][2], s_mu[cgl][3]);
   const float4 is = make_float4(s_is[cgl][0], s_is[cgl][1], s_is[cgl][2], s_is[cgl][3]);
   const float4 ga = *reinterpret_cast<const float4*>(gamma + cg * 4);
   const float4 be = *reinterpret_cast<const float4*>(beta + cg * 4);
-  for (int64_t r = rl; r < N; r += 32) {
+#pragma unroll 2
+  for (int64_t r = r0 + rl; r < r1; r += 32) {
     const int64_t e = r * C4 + cg;
     const float4 v = ld4<kBf16>(x, e);
     float4 o;
@@ -257,17 +308,20 @@ __global__ void __launch_bounds__(256) bn_small_fwd_kernel(const void* __restric
 }
 
 template <bool kBf16>
-__global__ void __launch_bounds__(256) bn_small_bwd_kernel(const void* __restrict__ x, const void* __restrict__ dy,
-                                                           const void* __restrict__ y, const float* __restrict__ mean,
-                                                           const float* __restrict__ invstd, const float* __restrict__ gamma,
-                                                           int relu, int64_t N, int C4, void* __restrict__ dx,
-                                                           void* __restrict__ dres, float* __restrict__ dgamma,
-                                                           float* __restrict__ dbeta, int accumulate) {
-  __shared__ double s_a[32][8][4], s_b[32][8][4];
+__global__ void __cluster_dims__(1, kSmallSplit, 1) __launch_bounds__(256)
+bn_small_bwd_kernel(const void* __restrict__ x, const void* __restrict__ dy, const void* __restrict__ y,
+                    const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
+                    int relu, int64_t N, int C4, void* __restrict__ dx, void* __restrict__ dres, float* __restrict__ dgamma,
+                    float* __restrict__ dbeta, int accumulate) {
+  namespace cgp = cooperative_groups;
+  __shared__ double s_w[8][2][8][4], s_t[2][8][4];
   __shared__ float s_dg[8][4], s_db[8][4];
   const int cgl = threadIdx.x & 7, rl = threadIdx.x >> 3;
   const int cg = blockIdx.x * 8 + cgl;
   const bool on = cg < C4;
+  const int64_t chunk = (N + kSmallSplit - 1) / kSmallSplit;
+  const int64_t r0 = (int64_t)blockIdx.y * chunk;
+  const int64_t r1 = (r0 + chunk < N) ? r0 + chunk : N;
   float4 mu = make_float4(0.f, 0.f, 0.f, 0.f), is = mu, ga = mu;
   if (on) {
     mu = *reinterpret_cast<const float4*>(mean + cg * 4);
@@ -284,7 +338,8 @@ __global__ void __launch_bounds__(256) bn_small_bwd_kernel(const void* __restric
   };
   double a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
   if (on) {
-    for (int64_t r = rl; r < N; r += 32) {
+#pragma unroll 2
+    for (int64_t r = r0 + rl; r < r1; r += 32) {
       const int64_t e = r * C4 + cg;
       const float4 v = ld4<kBf16>(x, e);
       const float4 g = dz_of(e);
@@ -293,25 +348,24 @@ __global__ void __launch_bounds__(256) bn_small_bwd_kernel(const void* __restric
       b[2] += (double)g.z * ((v.z - mu.z) * is.z); b[3] += (double)g.w * ((v.w - mu.w) * is.w);
     }
   }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) { s_a[rl][cgl][i] = a[i]; s_b[rl][cgl][i] = b[i]; }
-  __syncthreads();
-  if (rl == 0 && on) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      double sa = 0.0, sb = 0.0;
-      for (int r = 0; r < 32; ++r) { sa += s_a[r][cgl][i]; sb += s_b[r][cgl][i]; }
-      s_db[cgl][i] = (float)sa; s_dg[cgl][i] = (float)sb;
-      if (accumulate) { dbeta[cg * 4 + i] += (float)sa; dgamma[cg * 4 + i] += (float)sb; }
-      else { dbeta[cg * 4 + i] = (float)sa; dgamma[cg * 4 + i] = (float)sb; }
+  double sa, sb;
+  small_reduce(a, b, s_w, s_t, sa, sb);
+  if (threadIdx.x < 32) {
+    const int c = threadIdx.x & 7, i = threadIdx.x >> 3;
+    const int ch = (blockIdx.x * 8 + c) * 4 + i;
+    s_db[c][i] = (float)sa; s_dg[c][i] = (float)sb;
+    if (blockIdx.y == 0 && blockIdx.x * 8 + c < C4) {
+      if (accumulate) { dbeta[ch] += (float)sa; dgamma[ch] += (float)sb; }
+      else { dbeta[ch] = (float)sa; dgamma[ch] = (float)sb; }
     }
   }
-  __syncthreads();
+  cgp::this_cluster().sync();
   if (!on) return;
   const float inv_n = 1.0f / (float)N;
   const float4 dg = make_float4(s_dg[cgl][0], s_dg[cgl][1], s_dg[cgl][2], s_dg[cgl][3]);
   const float4 db = make_float4(s_db[cgl][0], s_db[cgl][1], s_db[cgl][2], s_db[cgl][3]);
-  for (int64_t r = rl; r < N; r += 32) {
+#pragma unroll 2
+  for (int64_t r = r0 + rl; r < r1; r += 32) {
     const int64_t e = r * C4 + cg;
     const float4 v = ld4<kBf16>(x, e);
     const float4 g = dz_of(e);
@@ -352,7 +406,7 @@ static int bn_fwd_t(const void* x, const void* res, const float* gamma, const fl
   if (workspace_bytes < pv2_bn_workspace_bytes(n, c)) return PV2_EWORKSPACE;
   const int nblk = nblocks_for(n), C4 = c / 4;
   if (n <= kSmallN) {
-    bn_small_fwd_kernel<kBf16><<<(C4 + 7) / 8, 256, 0, stream>>>(x, res, gamma, beta, running_mean, running_var, momentum, eps,
+    bn_small_fwd_kernel<kBf16><<<dim3((C4 + 7) / 8, kSmallSplit), 256, 0, stream>>>(x, res, gamma, beta, running_mean, running_var, momentum, eps,
                                                                 relu, n, C4, y, mean, invstd);
     PV2_DONE(1);
   }
@@ -379,7 +433,7 @@ static int bn_bwd_t(const void* x, const void* dy, const void* y, const float* g
   if (workspace_bytes < pv2_bn_workspace_bytes(n, c)) return PV2_EWORKSPACE;
   const int nblk = nblocks_for(n), C4 = c / 4;
   if (n <= kSmallN) {
-    bn_small_bwd_kernel<kBf16><<<(C4 + 7) / 8, 256, 0, stream>>>(x, dy, y, mean, invstd, gamma, relu, n, C4, dx, dres, dgamma,
+    bn_small_bwd_kernel<kBf16><<<dim3((C4 + 7) / 8, kSmallSplit), 256, 0, stream>>>(x, dy, y, mean, invstd, gamma, relu, n, C4, dx, dres, dgamma,
                                                                 dbeta, accumulate);
     PV2_DONE(1);
   }
