@@ -242,6 +242,7 @@ int pv2_field_sample_fwd(const float* vol, const float* pts, int64_t P, int Z, i
 int pv2_field_post_fwd(const float* vol, const float* pts, const float* dirs, int samples_per_ray, const float* u,
                        const float* f_r, const float* out_geo, int64_t geo_row, const float* Mr, const float* cr,
                        int64_t P, int Z, int Y, int X, int C, float* grad, float* rgb, void* stream);
+/* backward of the above; doutbar is [P, 72] (d sdf | d geo[64] | zeros: rows padded to a multiple of 8 channels) */
 int pv2_field_post_bwd(const float* vol, const float* pts, const float* dirs, int samples_per_ray, const float* f_r,
                        const float* out_geo, int64_t geo_row, const float* grad, const float* rgb, const float* Mr,
                        const float* g_rgb, const float* g_grad, const float* g_sdf, int64_t P, int Z, int Y, int X,

@@ -25,6 +25,8 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC",
     "--expt-relaxed-constexpr",
 ]
+if os.environ.get("PV2_MBAR_DEBUG") == "1":   # development: non-fatal barrier watchdog with a wait log (csrc/umma.cuh)
+    NVCC_FLAGS.append("-DPV2_MBAR_DEBUG")
 
 
 def _nvcc() -> str:

@@ -21,7 +21,10 @@ int pv2_spconv_gather_gemm_umma(const void*, const void*, int64_t, int64_t, cons
 // them through pv2_set_option.  Names: "gg_tma" (bf16 gather through TMA gather4: -1 auto by size, 0 off, 1 on),
 // "gg_bx3" (fp32 gather-GEMM as bf16x3: 0 / 1), "wgrad_mn" (MN-major bf16 weight-gradient kernel: 0 / 1).
 static int g_opt_gg_tma = -2, g_opt_gg_bx3 = -2, g_opt_wgrad_mn = -2, g_opt_ksplit_max = -2, g_opt_linear_bx3 = -2;
-static int g_opt_gg_groups = -2;   // "gg_groups": producer groups of the persistent fp32 gather-GEMM (2..4, 0 = default)
+static int g_opt_gg_groups = -2;
+static int g_opt_bx3_split = -2;  // "gg_bx3_split": deep levels on the split-K bf16x3 persistent kernel (0 / 1).  Default 0: measured
+// (profiles/r2v_micro_levels_*.txt) it gains 6 us at L2 64->64 and loses at L3 384->256 (74 -> 94 us) and L4 (30 -> 41 us):
+// the extra weight pre-split launch and the wider reduction outweigh the cheaper chunks; the step got slower (27.9 vs 26.7 ms)   // "gg_groups": producer groups of the persistent fp32 gather-GEMM (2..4, 0 = default)
 static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
 int pv2_get_option(const char* name) {
   if (name == nullptr) return -1;
@@ -29,6 +32,7 @@ int pv2_get_option(const char* name) {
   if (!strcmp(name, "gg_bx3")) { if (g_opt_gg_bx3 == -2) g_opt_gg_bx3 = env_int("PV2_GG_BX3", 1); return g_opt_gg_bx3; }
   if (!strcmp(name, "wgrad_mn")) { if (g_opt_wgrad_mn == -2) g_opt_wgrad_mn = env_int("PV2_WGRAD_MN", 1); return g_opt_wgrad_mn; }
   if (!strcmp(name, "linear_bx3")) { if (g_opt_linear_bx3 == -2) g_opt_linear_bx3 = env_int("PV2_LINEAR_BX3", 1); return g_opt_linear_bx3; }
+  if (!strcmp(name, "gg_bx3_split")) { if (g_opt_bx3_split == -2) g_opt_bx3_split = env_int("PV2_GG_BX3_SPLIT", 0); return g_opt_bx3_split; }
   if (!strcmp(name, "gg_groups")) { if (g_opt_gg_groups == -2) g_opt_gg_groups = env_int("PV2_GG_GROUPS", 0); return g_opt_gg_groups; }
   if (!strcmp(name, "gg_ksplit_max")) { if (g_opt_ksplit_max == -2) g_opt_ksplit_max = env_int("PV2_GG_KSPLIT_MAX", 0); return g_opt_ksplit_max; }
   return -1;
@@ -40,6 +44,7 @@ int pv2_set_option(const char* name, int value) {
   if (!strcmp(name, "wgrad_mn")) { g_opt_wgrad_mn = value; return 0; }
   if (!strcmp(name, "gg_ksplit_max")) { g_opt_ksplit_max = value; return 0; }
   if (!strcmp(name, "gg_groups")) { g_opt_gg_groups = value; return 0; }
+  if (!strcmp(name, "gg_bx3_split")) { g_opt_bx3_split = value; return 0; }
   if (!strcmp(name, "linear_bx3")) { g_opt_linear_bx3 = value; return 0; }
   return PV2_EINVAL;
 }

@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(256) field_post_fwd_kernel(const float* __rest
 // ---------------------------------------------------------------------------------------------------------------
 // Backward of field_post.  Per point:
 //   zbar = g_rgb * rgb (1 - rgb);  inbar = Mr^T zbar;  gbar = g_grad + inbar[0:3]          (total gradient on d sdf/d p)
-//   d f_r = inbar[3:67]  -> dF[:, cs:2cs];  d geo = inbar[67:131], d sdf = g_sdf  -> doutbar [P, 68]
+//   d f_r = inbar[3:67]  -> dF[:, cs:2cs];  d geo = inbar[67:131], d sdf = g_sdf  -> doutbar [P, 72] (68 used)
 //   ubar  = sum_i (dw_i . gbar) V_i[0:cs]  -> [P,64]  (second-order term: d grad / d u)
 //   dMr  += zbar (x) in,  dcr += zbar     (block partial sums, then atomics)
 __global__ void __launch_bounds__(256, 2) field_post_bwd_kernel(
@@ -225,15 +225,17 @@ __global__ void __launch_bounds__(256, 2) field_post_bwd_kernel(
       dge[i] = Ms[cg] * zb[0] + Ms[134 + cg] * zb[1] + Ms[268 + cg] * zb[2];
     }
     *reinterpret_cast<float4*>(dF + pt * dF_row + 64 + sub * 4) = make_float4(dfr[0], dfr[1], dfr[2], dfr[3]);
-    // doutbar row (68 wide, plain fp32): col 0 = d sdf, cols 1..64 = d geo, cols 65..67 = 0
+    // doutbar row (72 floats, plain fp32): col 0 = d sdf, cols 1..64 = d geo, cols 65..71 = 0 (the row is padded to a
+    // multiple of 8 channels so that the linears consuming it run on the bf16x3 tensor-core kernel)
     {
-      float* row = doutbar + pt * 68;
+      float* row = doutbar + pt * 72;
 #pragma unroll
       for (int i = 0; i < 4; ++i) { row[1 + sub * 4 + i] = dge[i]; ds[i] += dge[i]; }
       if (sub == 0) {
         row[0] = __ldg(g_sdf + pt);
         ds0 += row[0];
         row[65] = row[66] = row[67] = 0.f;
+        *reinterpret_cast<float4*>(row + 68) = make_float4(0.f, 0.f, 0.f, 0.f);
         gbar_out[pt * 3 + 0] = gb[0]; gbar_out[pt * 3 + 1] = gb[1]; gbar_out[pt * 3 + 2] = gb[2];
       }
     }

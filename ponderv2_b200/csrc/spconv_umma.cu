@@ -64,6 +64,7 @@ struct GGParams {
   void* y2;
   int64_t y2_row, y2_lo_off;
   int ablate;        // development only (PV2_GG_ABLATE): 1 skip the global loads, 2 skip split + st.shared, 4 skip the MMAs
+  int meta_bufs;     // persistent fp32 kernel: metadata buffers (2 or 3)
   int ksplit;        // > 1: gridDim.y CTAs share one row tile, each reduces a slice of the contraction and adds its
                      // partial result into the (pre-zeroed) output with red.global.add (small deep U-Net levels)
   // bf16x3 mode (persistent kernel): weights pre-split into bf16 hi / lo matrices [2][w2_rows][ktot64], fetched by TMA
@@ -603,7 +604,8 @@ __device__ __forceinline__ void split_store_bf16(uint32_t addr, uint32_t lo_delt
 //   so the producer warps only gather activations.
 // kG = producer groups (128 threads each; a group has one chunk in flight).  More groups did not help (r2p): the gathers
 // were not the critical path, the metadata preparation was (see the epilogue group below).
-template <bool kBx3, int kG = 2>
+// kNB = metadata buffers: 3 (prepared two tiles ahead) or 2 (wide layers, where a pipeline stage is worth more).
+template <bool kBx3, int kG, int kNB>
 __global__ void __launch_bounds__((kG * 4 + 5) * 32) umma_gather_gemm_persistent_kernel(const GGParams p, int num_tiles,
                                                                                         const __grid_constant__ CUtensorMap wmap) {
   constexpr int kPersistGroups = kG;
@@ -616,10 +618,11 @@ __global__ void __launch_bounds__((kG * 4 + 5) * 32) umma_gather_gemm_persistent
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b_bytes = p.n_pad * 128;
   const int stage_bytes = (kABytes + b_bytes) * 2;
-  const PersistLayout L = persist_layout(p.kvol, p.num_chunks, kMetaBufs);
+  constexpr int kMB = kNB;   // metadata buffers (NOT `nb`: the producers use that name for the 16-row weight blocks)
+  const PersistLayout L = persist_layout(p.kvol, p.num_chunks, kMB);
   uint8_t* stage_base = smem;
   uint8_t* meta_base = smem + (size_t)p.stages * stage_bytes;
-  uint32_t* kc_s = reinterpret_cast<uint32_t*>(meta_base + kMetaBufs * L.meta_bytes);
+  uint32_t* kc_s = reinterpret_cast<uint32_t*>(meta_base + kMB * L.meta_bytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(kc_s + p.num_chunks * 8);
   uint64_t* full_bar = bars;                        // [kMaxStages]  128 arrivals (the producing group)
   uint64_t* empty_bar = bars + kMaxStages;          // [kMaxStages]  tcgen05.commit
@@ -635,9 +638,13 @@ __global__ void __launch_bounds__((kG * 4 + 5) * 32) umma_gather_gemm_persistent
   auto meta_active = [&](int b) { return reinterpret_cast<uint16_t*>(meta_row(b) + kTileM); };
   auto meta_count = [&](int b) { return reinterpret_cast<int*>(meta_base + (size_t)b * L.meta_bytes + L.meta_bytes - 16); };
 
+  // split-K (p.ksplit > 1, the small deep levels): `num_tiles` counts VIRTUAL tiles = (row tile, contraction slice); a
+  // slice takes a contiguous share of the tile's active-chunk list and adds its partial sums into the pre-zeroed rows
+  const int ks = p.ksplit > 1 ? p.ksplit : 1;
   const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   // longest tiles (highest masks, last in tile order) first
-  auto tile_row0 = [&](int i) { return (int64_t)(num_tiles - 1 - ((int)blockIdx.x + i * (int)gridDim.x)) * kTileM; };
+  auto vtile = [&](int i) { return num_tiles - 1 - ((int)blockIdx.x + i * (int)gridDim.x); };
+  auto tile_row0 = [&](int i) { return (int64_t)(vtile(i) / ks) * kTileM; };
 
   if (tid == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(smem_u32(&full_bar[s]), 128); mbar_init(smem_u32(&empty_bar[s]), 1); }
@@ -682,11 +689,11 @@ __global__ void __launch_bounds__((kG * 4 + 5) * 32) umma_gather_gemm_persistent
     const uint64_t wstep = 16ull * p.w_sco32;
     int gbase = 0;   // global chunk counter at the start of the tile (same in every thread)
     for (int i = 0; i < my_tiles; ++i) {
-      const int b = i % kMetaBufs;
-      mbar_wait(smem_u32(&meta_full[b]), (uint32_t)(i / kMetaBufs) & 1u);
+      const int b = i % kMB;
+      mbar_wait(smem_u32(&meta_full[b]), (uint32_t)(i / kMB) & 1u);
       const int n_active = *meta_count(b);
       const int32_t* idx_s = meta_idx(b);
-      const uint16_t* active = meta_active(b);
+      const uint16_t* active = meta_active(b) + meta_count(b)[1];   // this slice's share of the list
       int it = (grp - gbase % kPersistGroups + kPersistGroups) % kPersistGroups;   // first chunk of this group in the tile
       for (; it < n_active; it += kPersistGroups) {
         const int g = gbase + it;
@@ -768,8 +775,8 @@ __global__ void __launch_bounds__((kG * 4 + 5) * 32) umma_gather_gemm_persistent
     const uint32_t idesc = make_idesc(kBx3 ? 1 : 2, kTileM, p.n_pad);
     int gbase = 0;
     for (int i = 0; i < my_tiles; ++i) {
-      const int b = i & 1, mb = i % kMetaBufs;
-      mbar_wait(smem_u32(&meta_full[mb]), (uint32_t)(i / kMetaBufs) & 1u);
+      const int b = i & 1, mb = i % kMB;
+      mbar_wait(smem_u32(&meta_full[mb]), (uint32_t)(i / kMB) & 1u);
       const int n_active = *meta_count(mb);
       mbar_wait(smem_u32(&tmem_empty[b]), ((uint32_t)(i >> 1) & 1u) ^ 1u);   // accumulator b drained (first two: free)
       tc_fence_after();
@@ -832,8 +839,8 @@ __global__ void __launch_bounds__((kG * 4 + 5) * 32) umma_gather_gemm_persistent
       }
     };
     auto finish = [&](int j) {
-      const int b = j % kMetaBufs;
-      mbar_wait(smem_u32(&meta_empty[b]), ((uint32_t)(j / kMetaBufs) & 1u) ^ 1u);
+      const int b = j % kMB;
+      mbar_wait(smem_u32(&meta_empty[b]), ((uint32_t)(j / kMB) & 1u) ^ 1u);
       int32_t* idx_s = meta_idx(b);
       int32_t* row_s = meta_row(b);
       uint16_t* active = meta_active(b);
@@ -887,16 +894,33 @@ __global__ void __launch_bounds__((kG * 4 + 5) * 32) umma_gather_gemm_persistent
         n_total += all;
         bar_sync_named(1, 128);
       }
-      if (et == 0) *meta_count(b) = n_total;
+      if (et == 0) {
+        int base = 0, cnt = n_total;
+        if (ks > 1) {
+          const int per = (n_total + ks - 1) / ks;
+          base = (vtile(j) % ks) * per;
+          if (base > n_total) base = n_total;
+          cnt = n_total - base;
+          if (cnt > per) cnt = per;
+        }
+        meta_count(b)[0] = cnt;
+        meta_count(b)[1] = base;
+      }
       bar_sync_named(1, 128);   // every epilogue thread's metadata writes are done
       if (et == 0) mbar_arrive(smem_u32(&meta_full[b]));
     };
+    constexpr int dist = kMB - 1;   // tiles of metadata lead
     if (my_tiles > 0) { issue(0); finish(0); }
-    if (my_tiles > 1) { issue(1); finish(1); }
+    if constexpr (kMB == 3) {
+      if (my_tiles > 1) { issue(1); finish(1); }
+    }
     for (int i = 0; i < my_tiles; ++i) {
-      const bool ahead = i + 2 < my_tiles;
-      if (ahead) issue(i + 2);
-      const int b = i & 1, mb = i % kMetaBufs;
+      const bool ahead = i + dist < my_tiles;
+      if (ahead) issue(i + dist);
+      if constexpr (kMB == 2) {
+        if (ahead) finish(i + dist);   // one buffer of lead: the next tile's metadata must not wait for this drain
+      }
+      const int b = i & 1, mb = i % kMB;
       mbar_wait(smem_u32(&tmem_full[b]), (uint32_t)(i >> 1) & 1u);
       tc_fence_after();
       const int n_active = *meta_count(mb);
@@ -913,18 +937,34 @@ __global__ void __launch_bounds__((kG * 4 + 5) * 32) umma_gather_gemm_persistent
           for (int q = 0; q < 16; ++q) v[q] = 0u;
         }
         if (j32 < 0) continue;
+        const bool first_slice = ks == 1 || (vtile(i) % ks) == 0;
         float f[16];
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
           const int co = col0 + q;
-          f[q] = __uint_as_float(v[q]) + ((p.bias != nullptr && co < p.cout) ? __ldg(&p.bias[co]) : 0.f);
+          f[q] = __uint_as_float(v[q]) + ((p.bias != nullptr && co < p.cout && first_slice) ? __ldg(&p.bias[co]) : 0.f);
+        }
+        if (ks > 1) {   // partial sums of this slice (act == 0 on this path): vector reductions into the pre-zeroed rows
+          if (n_active == 0 && !(first_slice && p.bias != nullptr)) continue;
+          float* yr = reinterpret_cast<float*>(p.y) + j * p.y_row + col0;
+          if ((col0 + 16 <= p.cout) && ((p.cout & 3) == 0)) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(yr + 4 * q), "f"(f[4 * q]),
+                           "f"(f[4 * q + 1]), "f"(f[4 * q + 2]), "f"(f[4 * q + 3]) : "memory");
+          } else {
+            for (int q = 0; q < 16 && col0 + q < p.cout; ++q) atomicAdd(yr + q, f[q]);
+          }
+          continue;
         }
         fp32_row_epilogue(p, f, j, col0);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&tmem_empty[b]));   // accumulator b may be overwritten
-      if (ahead) finish(i + 2);
+      if constexpr (kMB == 3) {
+        if (ahead) finish(i + dist);
+      }
     }
   }
   __syncthreads();
@@ -1260,45 +1300,71 @@ int launch_persistent(const GGParams& p0, cudaStream_t stream, const void* w2 = 
   while ((int)p.tmem_cols < 2 * p.n_pad) p.tmem_cols <<= 1;     // two accumulators
   if (p.tmem_cols > 512) return PV2_EUNSUPPORTED;
   const int stage_bytes = (kABytes + p.n_pad * 128) * 2;
-  const PersistLayout L = persist_layout(p.kvol, p.num_chunks, kMetaBufs);
+  PersistLayout L = persist_layout(p.kvol, p.num_chunks, kMetaBufs);
   int stages = (227 * 1024 - L.fixed) / stage_bytes;   // 227 KB: the opt-in maximum of dynamic shared memory per CTA
+  p.meta_bufs = kMetaBufs;
+  static int force_bufs = -1;
+  if (force_bufs < 0) { const char* e = getenv("PV2_GG_META_BUFS"); force_bufs = e ? atoi(e) : 0; }   // development switch
+  if (stages < 3 || force_bufs == 2) {   // wide layers: a stage is worth more than the third metadata buffer
+    L = persist_layout(p.kvol, p.num_chunks, 2);
+    stages = (227 * 1024 - L.fixed) / stage_bytes;
+    p.meta_bufs = 2;
+  }
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < kPersistGroups) return PV2_EUNSUPPORTED;          // groups <= stages (mbarrier parity aliasing)
   int groups = pv2_get_option("gg_groups");
   if (groups < 2 || groups > 4) groups = 2;   // measured (profiles/r2p_micro_levels_g{2,3,4}.txt): no difference
   if (!bx3 || stages < groups + 1) groups = 2;
   p.stages = stages;
-  p.ksplit = 1;
+  // split-K for the levels with fewer row tiles than SMs: ~one virtual tile per SM, at least 2 chunks per slice
+  int ksplit = 1;
+  if (bx3 && p0.ksplit == -1 && tiles * 2 <= PV2_SM_COUNT && p.act == 0 && !p.y_split && p.num_chunks >= 4) {
+    ksplit = (PV2_SM_COUNT + tiles - 1) / tiles;
+    if (ksplit > p.num_chunks / 2) ksplit = p.num_chunks / 2;
+    const int cap = pv2_get_option("gg_ksplit_max");
+    if (cap > 0 && ksplit > cap) ksplit = cap;
+    if (ksplit < 1) ksplit = 1;
+  }
+  p.ksplit = ksplit;
   p.ablate = 0;
   const size_t smem = (size_t)stages * stage_bytes + L.fixed;
-  const int grid = tiles < PV2_SM_COUNT ? tiles : PV2_SM_COUNT;
+  const int vtiles = tiles * ksplit;
+  const int grid = vtiles < PV2_SM_COUNT ? vtiles : PV2_SM_COUNT;
+  int launches = 1;
+  if (ksplit > 1) {
+    cudaMemset2DAsync(p.y, (size_t)p.y_row * sizeof(float), 0, (size_t)p.cout * sizeof(float), (size_t)p.n_out, stream);
+    ++launches;
+  }
   CUtensorMap wmap;
   memset(&wmap, 0, sizeof(wmap));
+  (void)groups;
+  cudaError_t e = cudaSuccess;
   if (bx3) {
     const int rc = encode_bf16_map(&wmap, w2, 2 * (int64_t)p.w2_rows, w2_cols, p.n_pad);
     if (rc != 0) return rc;
-    static bool done2[64] = {}, done3[64] = {}, done4[64] = {};
-    cudaError_t e = cudaSuccess;
-    if (groups == 4) {
-      e = ensure_smem_optin(umma_gather_gemm_persistent_kernel<true, 4>, done4);
+    static bool done3[64] = {}, done2[64] = {};
+    if (p.meta_bufs == 3) {
+      e = ensure_smem_optin(umma_gather_gemm_persistent_kernel<true, 2, 3>, done3);
       if (e != cudaSuccess) return (int)e;
-      umma_gather_gemm_persistent_kernel<true, 4><<<grid, (4 * 4 + 5) * 32, smem, stream>>>(p, tiles, wmap);
-    } else if (groups == 3) {
-      e = ensure_smem_optin(umma_gather_gemm_persistent_kernel<true, 3>, done3);
-      if (e != cudaSuccess) return (int)e;
-      umma_gather_gemm_persistent_kernel<true, 3><<<grid, (3 * 4 + 5) * 32, smem, stream>>>(p, tiles, wmap);
+      umma_gather_gemm_persistent_kernel<true, 2, 3><<<grid, kPersistThreads, smem, stream>>>(p, vtiles, wmap);
     } else {
-      e = ensure_smem_optin(umma_gather_gemm_persistent_kernel<true, 2>, done2);
+      e = ensure_smem_optin(umma_gather_gemm_persistent_kernel<true, 2, 2>, done2);
       if (e != cudaSuccess) return (int)e;
-      umma_gather_gemm_persistent_kernel<true, 2><<<grid, kPersistThreads, smem, stream>>>(p, tiles, wmap);
+      umma_gather_gemm_persistent_kernel<true, 2, 2><<<grid, kPersistThreads, smem, stream>>>(p, vtiles, wmap);
     }
   } else {
-    static bool done[64] = {};
-    cudaError_t e = ensure_smem_optin(umma_gather_gemm_persistent_kernel<false, 2>, done);
-    if (e != cudaSuccess) return (int)e;
-    umma_gather_gemm_persistent_kernel<false, 2><<<grid, kPersistThreads, smem, stream>>>(p, tiles, wmap);
+    static bool done3[64] = {}, done2[64] = {};
+    if (p.meta_bufs == 3) {
+      e = ensure_smem_optin(umma_gather_gemm_persistent_kernel<false, 2, 3>, done3);
+      if (e != cudaSuccess) return (int)e;
+      umma_gather_gemm_persistent_kernel<false, 2, 3><<<grid, kPersistThreads, smem, stream>>>(p, vtiles, wmap);
+    } else {
+      e = ensure_smem_optin(umma_gather_gemm_persistent_kernel<false, 2, 2>, done2);
+      if (e != cudaSuccess) return (int)e;
+      umma_gather_gemm_persistent_kernel<false, 2, 2><<<grid, kPersistThreads, smem, stream>>>(p, vtiles, wmap);
+    }
   }
-  PV2_DONE(1);
+  PV2_DONE(launches);
 }
 
 
@@ -1430,6 +1496,18 @@ static int fp32_groups(int cout, int kvol, int cin) {
   return (220 * 1024 - fixed) / stage_bytes >= 3 ? 3 : 2;
 }
 
+#ifdef PV2_MBAR_DEBUG
+extern "C" int pv2_debug_dump_waits(unsigned* out, int cap) {   // development only; not part of the ABI header
+  unsigned n = 0;
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(&n, pv2::g_wait_n, sizeof(n));
+  if (n > 2048) n = 2048;
+  if ((int)n > cap) n = cap;
+  cudaMemcpyFromSymbol(out, pv2::g_wait_log, (size_t)n * 16);
+  return (int)n;
+}
+#endif
+
 extern "C" {
 
 static int bx3_enabled() { return pv2_get_option("gg_bx3") != 0; }
@@ -1469,7 +1547,8 @@ int pv2_spconv_gather_gemm_umma(const void* x, const void* w, int64_t w_sco, int
   // deep levels keep the split-K 3xTF32 kernel); needs the pre-split weight workspace
   const int64_t tiles = (n_out + kTileM - 1) / kTileM;
   const int w2_rows = (cout + 15) / 16 * 16, w2_cols = (kvol * cin + 63) / 64 * 64;
-  bool bx3 = dtype == PV2_F32 && bx3_enabled() && (cin % 8) == 0 && tiles * 2 > PV2_SM_COUNT && workspace != nullptr &&
+  const bool small_ok = pv2_get_option("gg_bx3_split") > 0;   // split-K persistent kernel on the deep levels (off by default)
+  bool bx3 = dtype == PV2_F32 && bx3_enabled() && (cin % 8) == 0 && (tiles * 2 > PV2_SM_COUNT || small_ok) && workspace != nullptr &&
              workspace_bytes >= pv2_spconv_workspace_bytes(n_in, cin, cout, kvol, dtype) && ((uintptr_t)workspace & 127) == 0 &&
              tensor_map_encoder() != nullptr;
   if (bx3) {
@@ -1486,7 +1565,9 @@ int pv2_spconv_gather_gemm_umma(const void* x, const void* w, int64_t w_sco, int
     q.y = (char*)y + (size_t)co0 * eb;
     if (bx3) {
       q.w2_row0 = co0; q.w2_rows = w2_rows;
+      q.ksplit = -1;   // auto: split the contraction when the row tiles do not fill the SMs
       const int rp = launch_persistent(q, stream, workspace, w2_cols);
+      q.ksplit = 0;
       if (rp == 0) continue;
       if (rp != PV2_EUNSUPPORTED) return rp;
     }

@@ -16,6 +16,12 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+#ifdef PV2_MBAR_DEBUG
+// Development build (PV2_MBAR_DEBUG): a wait that times out records (block, thread, barrier address, parity) and RETURNS,
+// so that the kernel drains and the host can read who was waiting for what (pv2_debug_dump_waits).
+static __device__ unsigned g_wait_log[4 * 2048];
+static __device__ unsigned g_wait_n;
+#endif
 // Bounded wait (~2 s of SM clocks): a protocol bug becomes a trap (launch error) instead of a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
@@ -29,7 +35,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity)
         : "memory");
     if (done) return;
+#ifdef PV2_MBAR_DEBUG
+    if (clock64() - t0 > 200000000LL) {
+      if ((threadIdx.x & 31) == 0) {
+        const unsigned i = atomicAdd(&g_wait_n, 1u);
+        if (i < 2048) { g_wait_log[4 * i] = blockIdx.x; g_wait_log[4 * i + 1] = threadIdx.x; g_wait_log[4 * i + 2] = bar; g_wait_log[4 * i + 3] = parity; }
+      }
+      return;
+    }
+#else
     if (clock64() - t0 > 4000000000LL) __trap();
+#endif
   }
 }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }

@@ -125,7 +125,7 @@ class FusedFieldFunction(torch.autograd.Function):
         g_sdf, g_grad, g_rgb = z(g_sdf, (P,)), z(g_grad, (P, 3)), z(g_rgb, (P, 3))
         gbar = torch.empty((P, 3), dtype=torch.float32, device=dev)
         dF = torch.empty((P, 128), dtype=torch.float32, device=dev)
-        doutbar = torch.empty((P, 68), dtype=torch.float32, device=dev)
+        doutbar = torch.empty((P, 72), dtype=torch.float32, device=dev)   # 68 used, rows padded to 8 channels
         ubar = torch.empty((P, 64), dtype=torch.float32, device=dev)
         small = torch.zeros(3 * 134 + 3 + 64 + 68, dtype=torch.float32, device=dev)   # one fill for the four accumulators
         dMr, dcr = small[:402].view(3, 134), small[402:405]
@@ -143,10 +143,10 @@ class FusedFieldFunction(torch.autograd.Function):
         _linear(ubar, 64, 0, False, wp.t().contiguous(), None, hbar, 128, 0, False, 2, s, 128, 0, P, 64, 128)
         d_wp = _dense_wgrad(s, 128, 0, ubar, 64, 0, P, 128, 64)
         # through out = [a | f_s] wcat^T + c1:  hbar += (doutbar wcat[:, :128]) * s   [epilogue 3];  dF[:, :64] = doutbar wcat[:, 128:]
-        wcat_t = wcat.t().contiguous()                                    # [192, 68]
-        _linear(doutbar, 68, 0, False, wcat_t[:128], None, hbar, 128, 0, False, 3, s, 128, 0, P, 68, 128)
-        _linear(doutbar, 68, 0, False, wcat_t[128:], None, dF, 128, 0, False, 0, None, 0, 0, P, 68, 64)
-        d_wcat = _dense_wgrad(xa, 192, 0, doutbar, 68, 0, P, 192, 68)
+        wcat_t = torch.nn.functional.pad(wcat.t(), (0, 4))                # [192, 72], zero columns against the row padding
+        _linear(doutbar, 72, 0, False, wcat_t[:128], None, hbar, 128, 0, False, 3, s, 128, 0, P, 72, 128)
+        _linear(doutbar, 72, 0, False, wcat_t[128:], None, dF, 128, 0, False, 0, None, 0, 0, P, 72, 64)
+        d_wcat = _dense_wgrad(xa, 192, 0, doutbar, 72, 0, P, 192, 68)
         # through a = softplus(h), h = f_s M0^T + c0:  dF[:, :64] += hbar M0   [epilogue 4]
         _linear(hbar, 128, 0, False, M0.t().contiguous(), None, dF, 128, 0, False, 4, None, 0, 0, P, 128, 64)
         d_M0 = _dense_wgrad(xa[:, 128:], 192, 0, hbar, 128, 0, P, 64, 128)

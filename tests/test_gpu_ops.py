@@ -625,6 +625,34 @@ def test_full_size_conv_matches_oracle(cuda_lib, cin, cout):
         assert v < 1e-4, (k, v, errs)
 
 
+def test_full_size_stem_conv_matches_oracle(cuda_lib):
+    """The 5^3 stem (spconv_unet_v1m1_base.py:111-119: 6 -> 32 channels, 125 offsets) at the 100 k-voxel size: the
+    persistent kernel with two metadata buffers (125 x 128 neighbour indices per tile) and the zero-padded 6 -> 8 input
+    channels, forward and weight gradient against the fp64 oracle."""
+    import ponderv2_b200.spconv.pytorch as spconv
+    from tests.conftest import record
+    dev = _dev()
+    n = 100_000
+    ind, shape = _indoor_indices(n, 2000)
+    torch.manual_seed(11)
+    mod = spconv.SubMConv3d(6, 32, 5, padding=1, bias=False, indice_key="stem").to(dev)
+    with torch.no_grad():
+        mod.weight.normal_(0.0, 0.05)
+    x64 = torch.randn(n, 6, dtype=torch.float64)
+    g64 = torch.randn(n, 32, dtype=torch.float64)
+    out = mod(spconv.SparseConvTensor(x64.to(dev, torch.float32), torch.from_numpy(ind).to(dev), shape, 1)).features
+    out.backward(g64.to(dev, torch.float32))
+    w64 = mod.weight.detach().cpu().double().requires_grad_(True)
+    yo = so.subm_conv(so.OracleSparseTensor(x64, ind, shape, 1), w64, None, 5, "stem").features
+    yo.backward(g64)
+    scale = lambda t: max(t.abs().max().item(), 1e-6)
+    errs = {"y": (out.detach().cpu().double() - yo.detach()).abs().max().item() / scale(yo),
+            "dw": (mod.weight.grad.cpu().double() - w64.grad).abs().max().item() / scale(w64.grad)}
+    record("full_size_stem_conv_matches_oracle", **errs)
+    for k, v in errs.items():
+        assert v < 1e-4, (k, v, errs)
+
+
 @pytest.mark.parametrize("cin,cout,tma", [(64, 64, 1), (128, 64, 1), (64, 128, 0), (256, 256, 1), (96, 96, 0)])
 def test_full_size_conv_bf16_matches_oracle(cuda_lib, cin, cout, tma):
     """bf16 storage at the BASELINE size (100 k voxels): forward, data gradient and weight gradient against the fp64
