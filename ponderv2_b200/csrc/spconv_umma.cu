@@ -1305,7 +1305,9 @@ int launch_persistent(const GGParams& p0, cudaStream_t stream, const void* w2 = 
   p.meta_bufs = kMetaBufs;
   static int force_bufs = -1;
   if (force_bufs < 0) { const char* e = getenv("PV2_GG_META_BUFS"); force_bufs = e ? atoi(e) : 0; }   // development switch
-  if (stages < 3 || force_bufs == 2) {   // wide layers: a stage is worth more than the third metadata buffer
+  // two buffers only where three leave fewer than two stages (Cout = 256, the 125-offset stem); measured in one run
+  // (profiles/r2y_micro_levels_mb{0,3}.txt): 96 -> 128 data gradient 146 us with 3 buffers / 2 stages, 158 us with 2 / 3
+  if (stages < kPersistGroups || force_bufs == 2) {
     L = persist_layout(p.kvol, p.num_chunks, 2);
     stages = (227 * 1024 - L.fixed) / stage_bytes;
     p.meta_bufs = 2;
