@@ -28,6 +28,7 @@ from a calibration step so that the whole run stays within a few minutes.
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import statistics
@@ -299,8 +300,10 @@ def cpu_oracle_step(wl: dict, frac: float, threads: int) -> dict:
 def config_dict(wl: dict, world: int) -> dict:
     """Identical keys from both arms."""
     return {"workload": wl["name"], "scenes_per_gpu_per_step": 1, "parallelism": f"dp{world}",
-            "projection": "SimpleConv3D-v1m1 (the nuScenes config's projection; the ScanNet config's UNet3D-v1m2 is "
-                          "SURVEY 8f-1)",
+            "projection": ("UNet3D-v1m2 (the ScanNet config's projection, SURVEY 8f-1; cuDNN)"
+                           if wl.get("projection") == "UNet3D-v1m2" else
+                           "SimpleConv3D-v1m1 (the nuScenes config's projection; --projection unet3d runs the ScanNet "
+                           "config's UNet3D-v1m2, SURVEY 8f-1)"),
             "l2": "per-step working set (dense volumes, render activations) exceeds the 126 MB L2"}
 
 
@@ -353,7 +356,8 @@ def build_model(wl: dict, dev, overlap: bool = True):
                                   grid_shape=wl["grid_shape"], grid_size=(0.6, 0.6, 1.6)).to(dev).train()
     else:
         model = PonderIndoorStep(backbone=dict(in_channels=6, num_classes=0), renderer=renderer_cfg(wl["s0"], wl["si"]),
-                                 projection=dict(in_channels=96, out_channels=128), grid_shape=wl["grid_shape"],
+                                 projection=dict(type=wl.get("projection", "SimpleConv3D-v1m1"), in_channels=96,
+                                                 out_channels=128), grid_shape=wl["grid_shape"],
                                  grid_size=0.02).to(dev).train()
     # flat buffers in backward-completion order: renderer, projection, then the backbone back to front
     flat = FlatParameters(model, order=model.grad_completion_order(), num_chunks=4)
@@ -461,6 +465,11 @@ def run_ours(args, wl: dict) -> None:
             # mappings alive), which otherwise land in the first timed steps (r2o: c3 at N = 2, 43.8 vs 37.7 ms/step)
             for _ in range(2):
                 step({k: v.to(dev, non_blocking=True) for k, v in host.items()})
+        # the host enqueues ~1000 launches per step and is within 20 % of the device time: a generation-2 garbage collection
+        # inside the K steps (tens of ms) shows up as +2 ms/step (r2y: 30.2 vs 27.9 ms in two runs of the same binary), so
+        # collect before and keep the collector off for the timed region, as training loops that manage GC themselves do
+        gc.collect()
+        gc.disable()
         barrier()
         l0 = lib.pv2_launch_count()
         if profile:
@@ -475,6 +484,7 @@ def run_ours(args, wl: dict) -> None:
                 loss = step(resident)
         e1.record()
         barrier()
+        gc.enable()
         _lib.PROFILE.stop()
         ms = e0.elapsed_time(e1)
         t = torch.tensor([ms], device=dev)
@@ -578,13 +588,23 @@ def main() -> None:
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--projection", default="simple", choices=["simple", "unet3d"],
+                    help="indoor workloads: dense projection network. simple = SimpleConv3D-v1m1 (default, the step the "
+                         "round-1 numbers and the CPU arm are quoted on); unet3d = UNet3D-v1m2, the ScanNet config's own "
+                         "(configs/scannet/pretrain-ponder-spunet-v1m1-0-base.py:26-30; cuDNN, GPU arm only)")
     ap.add_argument("--no-overlap", action="store_true",
                     help="N > 1: one all-reduce of the whole flat gradient buffer after backward instead of chunked "
                          "all-reduces overlapped with it (A/B switch)")
     ap.add_argument("--profile-step", action="store_true",
                     help="run one warmed-up step inside cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)")
     args = ap.parse_args()
-    wl = WORKLOADS[args.workload]
+    wl = dict(WORKLOADS[args.workload])
+    if args.projection == "unet3d":
+        if wl["outdoor"] or args.impl == "reference":
+            raise SystemExit("--projection unet3d: indoor workloads, GPU arm only")
+        wl["projection"] = "UNet3D-v1m2"
+        wl["name"] += ", UNet3D-v1m2 projection"
+        args.no_cpu_baseline = True
     if args.impl == "reference":
         run_reference(args, wl)
     else:

@@ -96,8 +96,12 @@ class PonderIndoorStep(nn.Module):
             raise NotImplementedError("pool_type: every shipped config uses 'mean'")
         bb = dict(backbone); bb.pop("type", None)
         self.backbone = SpUNetBase(**bb)
-        proj = dict(projection or dict(in_channels=96, out_channels=128)); proj.pop("type", None)
-        self.proj_net = SimpleConv3D(**proj).to(memory_format=torch.channels_last_3d)
+        proj = dict(projection or dict(in_channels=96, out_channels=128))
+        if proj.pop("type", "SimpleConv3D-v1m1") == "UNet3D-v1m2":   # the ScanNet / S3DIS configs' projection (§8f-1)
+            from .models import UNet3Dv1m2
+            self.proj_net = UNet3Dv1m2(**proj).to(memory_format=torch.channels_last_3d)
+        else:
+            self.proj_net = SimpleConv3D(**proj).to(memory_format=torch.channels_last_3d)
         self.renderer = build_renderer(renderer)
         self.grid_shape = tuple(int(g) for g in grid_shape)
         self.grid_size = float(grid_size)
