@@ -953,7 +953,9 @@ __global__ void __launch_bounds__((kG * 4 + 5) * 32) umma_gather_gemm_persistent
               asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(yr + 4 * q), "f"(f[4 * q]),
                            "f"(f[4 * q + 1]), "f"(f[4 * q + 2]), "f"(f[4 * q + 3]) : "memory");
           } else {
-            for (int q = 0; q < 16 && col0 + q < p.cout; ++q) atomicAdd(yr + q, f[q]);
+#pragma unroll
+            for (int q = 0; q < 16; ++q)   // (static indices: a run-time loop here put f[] into local memory, +7 % on L0)
+              if (col0 + q < p.cout) atomicAdd(yr + q, f[q]);
           }
           continue;
         }
