@@ -204,7 +204,7 @@ def profiled_traffic(kernel_prefix: str):
             continue
         tot_b = tot_n = 0
         for name, v in d.get("kernels", {}).items():
-            if name.startswith(kernel_prefix):
+            if name.startswith(kernel_prefix) and "[render linear]" not in name:
                 tot_b += v["dram_bytes_total"]; tot_n += v["launches"]
         if tot_n:
             best = dict(bytes_per_launch=tot_b / tot_n, source=f"profiles/{f.name}")

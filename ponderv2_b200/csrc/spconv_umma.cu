@@ -114,29 +114,68 @@ __device__ __forceinline__ void split_store(uint32_t addr, uint32_t lo_delta, co
 // predicated-off FADD on a just-loaded register still waits for the load, which serialises the gather.
 // fp32 output of one row's 16 accumulator columns [col0, col0 + 16): fused activation / backward epilogues, then plain or
 // split-precision stores.  (bias already added)
-__device__ __forceinline__ void fp32_row_epilogue(const GGParams& p, float (&f)[16], int64_t j, int col0) {
+// operands of the backward epilogues (act >= 2) for one row's columns [col0, col0 + 16): s = y2 (act 2, 3), y_old (3, 4)
+__device__ __forceinline__ void epilogue_operands(const GGParams& p, int64_t j, int col0, float (&sa)[16], float (&so)[16]) {
+  const float* ar = reinterpret_cast<const float*>(p.y2) + j * p.y2_row + col0;
+  const float* yo = reinterpret_cast<const float*>(p.y) + j * p.y_row + col0;
+  const bool vec = (col0 + 16 <= p.cout) && ((p.cout & 3) == 0) && ((p.y_row & 3) == 0) && ((p.y2_row & 3) == 0);
+  if (vec) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), o = a;
+      if (p.act != 4) a = __ldg(reinterpret_cast<const float4*>(ar) + q);
+      if (p.act != 2) o = *(reinterpret_cast<const float4*>(yo) + q);
+      sa[4 * q] = a.x; sa[4 * q + 1] = a.y; sa[4 * q + 2] = a.z; sa[4 * q + 3] = a.w;
+      so[4 * q] = o.x; so[4 * q + 1] = o.y; so[4 * q + 2] = o.z; so[4 * q + 3] = o.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const bool in = col0 + i < p.cout;
+      sa[i] = (in && p.act != 4) ? __ldg(ar + i) : 0.f;
+      so[i] = (in && p.act != 2) ? yo[i] : 0.f;
+    }
+  }
+}
+
+// pre_a / pre_y: the act >= 2 operands already in registers (the persistent kernel fetches them one column block ahead).
+// kActs = false compiles the activation epilogues out (sparse convolutions: act is always 0).
+template <bool kActs = true>
+__device__ __forceinline__ void fp32_row_epilogue(const GGParams& p, float (&f)[16], int64_t j, int col0,
+                                                  const float* pre_a = nullptr, const float* pre_y = nullptr) {
   float g2[16];
-  if (p.act == 1) {
+  if (kActs && p.act == 1) {
+    // softplus(beta = 100) and its derivative sigmoid(100 h) from ONE fast exponential: e = exp(-|t|) in (0, 1];
+    // softplus = max(h, 0) + log(1 + e) / 100, sigmoid = (t >= 0 ? 1 : e) / (1 + e).  (ex2 / lg2 approximations: absolute
+    // error of log(1 + e) <= 2e-7, i.e. 2e-9 on h-scale values; the libm expf + log1pf pair cost ~150 instructions per
+    // element and made the four epilogue warps the bottleneck of the layer: 910 us for 524 k rows, profiles/r2za_launches.csv)
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       const float t = 100.f * f[i];
-      g2[i] = 1.f / (1.f + __expf(-t));
-      f[i] = (t > 20.f) ? f[i] : log1pf(expf(t)) * 0.01f;
+      const float e = __expf(-fabsf(t));
+      const float r = __fdividef(1.f, 1.f + e);
+      g2[i] = (t >= 0.f) ? r : e * r;
+      f[i] = fmaxf(f[i], 0.f) + __logf(1.f + e) * 0.01f;
     }
   }
   const bool vec = (col0 + 16 <= p.cout) && ((p.cout & 3) == 0);
-  if (p.act >= 2) {
+  if (kActs && p.act >= 2) {
     // backward-pass epilogues of the SDF decoder (y2 is an INPUT here, plain fp32, row stride y2_row):
     //   2: y = v * 100 s (1 - s)       (through the softplus derivative s = sigmoid(100 h))
     //   3: y = y_old + v * s           4: y = y_old + v
-    const float* ar = reinterpret_cast<const float*>(p.y2) + j * p.y2_row + col0;
-    const float* yo = reinterpret_cast<const float*>(p.y) + j * p.y_row + col0;
+    float sa[16], so[16];
+    if (pre_a != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { sa[i] = pre_a[i]; so[i] = pre_y[i]; }
+    } else {
+      epilogue_operands(p, j, col0, sa, so);
+    }
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       if (col0 + i < p.cout) {
-        if (p.act == 2) { const float sg = __ldg(ar + i); f[i] *= 100.f * sg * (1.f - sg); }
-        else if (p.act == 3) f[i] = yo[i] + f[i] * __ldg(ar + i);
-        else f[i] += yo[i];
+        if (p.act == 2) f[i] *= 100.f * sa[i] * (1.f - sa[i]);
+        else if (p.act == 3) f[i] = so[i] + f[i] * sa[i];
+        else f[i] += so[i];
       }
     }
   }
@@ -166,7 +205,7 @@ __device__ __forceinline__ void fp32_row_epilogue(const GGParams& p, float (&f)[
     }
   };
   store(reinterpret_cast<float*>(p.y), p.y_row, p.y_lo_off, f, p.y_split != 0);
-  if (p.act == 1 && p.y2 != nullptr) store(reinterpret_cast<float*>(p.y2), p.y2_row, p.y2_lo_off, g2, p.y_split != 0);
+  if (kActs && p.act == 1 && p.y2 != nullptr) store(reinterpret_cast<float*>(p.y2), p.y2_row, p.y2_lo_off, g2, p.y_split != 0);
 }
 
 // 16 zero bytes in global memory: missing neighbours / padding rows load from here instead of predicating the load and
@@ -605,7 +644,10 @@ __device__ __forceinline__ void split_store_bf16(uint32_t addr, uint32_t lo_delt
 // kG = producer groups (128 threads each; a group has one chunk in flight).  More groups did not help (r2p): the gathers
 // were not the critical path, the metadata preparation was (see the epilogue group below).
 // kNB = metadata buffers: 3 (prepared two tiles ahead) or 2 (wide layers, where a pipeline stage is worth more).
-template <bool kBx3, int kG, int kNB>
+// kLin = dense linear layer (identity row map, kvol = 1, fused activation epilogues of the render MLP); false = sparse
+// convolution (act = 0): the two have different register budgets in the epilogue group (27 neighbour indices in flight per
+// row vs. prefetched epilogue operands), so they are separate instantiations.
+template <bool kBx3, int kG, int kNB, bool kLin>
 __global__ void __launch_bounds__((kG * 4 + 5) * 32) umma_gather_gemm_persistent_kernel(const GGParams p, int num_tiles,
                                                                                         const __grid_constant__ CUtensorMap wmap) {
   constexpr int kPersistGroups = kG;
@@ -824,7 +866,7 @@ __global__ void __launch_bounds__((kG * 4 + 5) * 32) umma_gather_gemm_persistent
     // latency, and `finish(j)` stores them and compacts the active-chunk list.  (ncu, profiles/r2q_gg32: with the whole
     // preparation done back to back before each drain, producers and the MMA warp spent 18 % of all warp samples
     // waiting for the next tile's metadata - the epilogue group was the critical path of the kernel.)
-    constexpr int kRegIdx = 27;
+    constexpr int kRegIdx = kLin ? 1 : 27;
     int32_t pre_row = -1;
     int32_t pre_idx[kRegIdx];
     auto issue = [&](int j) {
@@ -927,7 +969,8 @@ __global__ void __launch_bounds__((kG * 4 + 5) * 32) umma_gather_gemm_persistent
       const int32_t j32 = meta_row(mb)[lg * 32 + lane];
       const int64_t j = j32;
       const uint32_t acc = tmem_base + (uint32_t)b * acc_stride + ((uint32_t)(lg * 32) << 16);
-      for (int col0 = 0; col0 < p.n_pad; col0 += 16) {
+      // one block of 16 accumulator columns of this thread's row: TMEM -> registers -> epilogue -> global
+      auto drain_block = [&](int col0, const float* pa, const float* py) {
         uint32_t v[16];
         if (n_active > 0) {
           tmem_ld_x16(acc + (uint32_t)col0, v);
@@ -936,7 +979,7 @@ __global__ void __launch_bounds__((kG * 4 + 5) * 32) umma_gather_gemm_persistent
 #pragma unroll
           for (int q = 0; q < 16; ++q) v[q] = 0u;
         }
-        if (j32 < 0) continue;
+        if (j32 < 0) return;
         const bool first_slice = ks == 1 || (vtile(i) % ks) == 0;
         float f[16];
 #pragma unroll
@@ -945,7 +988,7 @@ __global__ void __launch_bounds__((kG * 4 + 5) * 32) umma_gather_gemm_persistent
           f[q] = __uint_as_float(v[q]) + ((p.bias != nullptr && co < p.cout && first_slice) ? __ldg(&p.bias[co]) : 0.f);
         }
         if (ks > 1) {   // partial sums of this slice (act == 0 on this path): vector reductions into the pre-zeroed rows
-          if (n_active == 0 && !(first_slice && p.bias != nullptr)) continue;
+          if (n_active == 0 && !(first_slice && p.bias != nullptr)) return;
           float* yr = reinterpret_cast<float*>(p.y) + j * p.y_row + col0;
           if ((col0 + 16 <= p.cout) && ((p.cout & 3) == 0)) {
 #pragma unroll
@@ -957,9 +1000,25 @@ __global__ void __launch_bounds__((kG * 4 + 5) * 32) umma_gather_gemm_persistent
             for (int q = 0; q < 16; ++q)   // (static indices: a run-time loop here put f[] into local memory, +7 % on L0)
               if (col0 + q < p.cout) atomicAdd(yr + q, f[q]);
           }
-          continue;
+          return;
         }
-        fp32_row_epilogue(p, f, j, col0);
+        fp32_row_epilogue<kLin>(p, f, j, col0, pa, py);
+      };
+      if (kLin && p.act >= 2 && j32 >= 0) {
+        // backward epilogues of the render MLP read one or two more [rows, Cout] operands: fetched ONE column block ahead
+        // as 128-bit loads into two alternating register sets, so that the (dependent, scalar) loads no longer serialise
+        // the drain (r2za: 0.9 - 1.35 ms per such layer at 524 k rows = 0.7 TB/s)
+        float a0[16], y0[16], a1[16], y1[16];
+        epilogue_operands(p, j, 0, a0, y0);
+        for (int col0 = 0; col0 < p.n_pad; col0 += 32) {
+          const bool second = col0 + 16 < p.n_pad;
+          if (second) epilogue_operands(p, j, col0 + 16, a1, y1);
+          drain_block(col0, a0, y0);
+          if (col0 + 32 < p.n_pad) epilogue_operands(p, j, col0 + 32, a0, y0);
+          if (second) drain_block(col0 + 16, a1, y1);
+        }
+      } else {
+        for (int col0 = 0; col0 < p.n_pad; col0 += 16) drain_block(col0, nullptr, nullptr);
       }
       tc_fence_before();
       __syncwarp();
@@ -1343,30 +1402,26 @@ int launch_persistent(const GGParams& p0, cudaStream_t stream, const void* w2 = 
   memset(&wmap, 0, sizeof(wmap));
   (void)groups;
   cudaError_t e = cudaSuccess;
+  const bool linear = p.nbr == nullptr && p.kvol == 1;   // pv2_linear: identity map, activation epilogues
   if (bx3) {
     const int rc = encode_bf16_map(&wmap, w2, 2 * (int64_t)p.w2_rows, w2_cols, p.n_pad);
     if (rc != 0) return rc;
     static bool done3[64] = {}, done2[64] = {};
-    if (p.meta_bufs == 3) {
-      e = ensure_smem_optin(umma_gather_gemm_persistent_kernel<true, 2, 3>, done3);
-      if (e != cudaSuccess) return (int)e;
-      umma_gather_gemm_persistent_kernel<true, 2, 3><<<grid, kPersistThreads, smem, stream>>>(p, vtiles, wmap);
-    } else {
-      e = ensure_smem_optin(umma_gather_gemm_persistent_kernel<true, 2, 2>, done2);
-      if (e != cudaSuccess) return (int)e;
-      umma_gather_gemm_persistent_kernel<true, 2, 2><<<grid, kPersistThreads, smem, stream>>>(p, vtiles, wmap);
-    }
+#define PV2_LAUNCH_PERSIST(BX, NB, LIN, FLAGS)                                                                       \
+  do {                                                                                                              \
+    e = ensure_smem_optin(umma_gather_gemm_persistent_kernel<BX, 2, NB, LIN>, FLAGS);                               \
+    if (e != cudaSuccess) return (int)e;                                                                            \
+    umma_gather_gemm_persistent_kernel<BX, 2, NB, LIN><<<grid, kPersistThreads, smem, stream>>>(p, vtiles, wmap);   \
+  } while (0)
+    static bool d3l[64] = {}, d2l[64] = {};
+    if (linear) { if (p.meta_bufs == 3) PV2_LAUNCH_PERSIST(true, 3, true, d3l); else PV2_LAUNCH_PERSIST(true, 2, true, d2l); }
+    else { if (p.meta_bufs == 3) PV2_LAUNCH_PERSIST(true, 3, false, done3); else PV2_LAUNCH_PERSIST(true, 2, false, done2); }
   } else {
     static bool done3[64] = {}, done2[64] = {};
-    if (p.meta_bufs == 3) {
-      e = ensure_smem_optin(umma_gather_gemm_persistent_kernel<false, 2, 3>, done3);
-      if (e != cudaSuccess) return (int)e;
-      umma_gather_gemm_persistent_kernel<false, 2, 3><<<grid, kPersistThreads, smem, stream>>>(p, vtiles, wmap);
-    } else {
-      e = ensure_smem_optin(umma_gather_gemm_persistent_kernel<false, 2, 2>, done2);
-      if (e != cudaSuccess) return (int)e;
-      umma_gather_gemm_persistent_kernel<false, 2, 2><<<grid, kPersistThreads, smem, stream>>>(p, vtiles, wmap);
-    }
+    static bool d3l[64] = {}, d2l[64] = {};
+    if (linear) { if (p.meta_bufs == 3) PV2_LAUNCH_PERSIST(false, 3, true, d3l); else PV2_LAUNCH_PERSIST(false, 2, true, d2l); }
+    else { if (p.meta_bufs == 3) PV2_LAUNCH_PERSIST(false, 3, false, done3); else PV2_LAUNCH_PERSIST(false, 2, false, done2); }
+#undef PV2_LAUNCH_PERSIST
   }
   PV2_DONE(launches);
 }

@@ -9,4 +9,4 @@ for w in c3 c4; do
 timeout 900 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --workload $w > $out/${tag}_bench_$w.json 2> $out/${tag}_bench_$w.log; echo "bench $w exit $?"; grep loop $out/${tag}_bench_$w.log
 done
 timeout 600 python tools/host_overhead.py --steps 10 > $out/${tag}_host_overhead.json 2> $out/${tag}_host_overhead.log
-bash tools/r2_ncu_step.sh $tag umma_gather_gemm_persistent bn_small_bwd insert_down umma_wgrad_mn
+bash tools/r2_ncu_step.sh $tag "umma_gather_gemm_persistent_kernel<1, 2, 3, 1>"

@@ -6,8 +6,21 @@ path, out = sys.argv[1], sys.argv[2]
 lines = [l for l in open(path) if not l.startswith("==")]
 agg = collections.defaultdict(lambda: dict(launches=0, us=0.0, dram_bytes=0.0))
 seen = set()
+# The render MLP's linear layers run on the same tensor-core kernels as the sparse convolutions (identity row map).  They
+# are told apart by position in the launch list: forward linears sit between field_sample_fwd and ray_resample /
+# field_post_fwd, backward linears between field_post_bwd and field_sample_bwd.  Their launches are booked under
+# "<kernel> [render linear]" so that the sparse-conv traffic (bench.py's roofline family) is not mixed with them.
+in_render, last_id = False, None
 for r in csv.DictReader(lines):
     name = r["Kernel Name"].split("(")[0].replace("void ", "").replace("<unnamed>::", "")
+    if r.get("ID") != last_id:
+        last_id = r.get("ID")
+        if "field_sample_fwd" in name or "field_post_bwd" in name:
+            in_render = True
+        elif "ray_resample" in name or "field_post_fwd" in name or "field_sample_bwd" in name or "ray_composite" in name:
+            in_render = False
+    if in_render and "umma_gather_gemm" in name:
+        name += " [render linear]"
     try:
         v = float(r["Metric Value"].replace(",", ""))
     except ValueError:
