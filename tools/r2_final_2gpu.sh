@@ -6,4 +6,3 @@ run() { name=$1; shift; timeout 900 python -m torch.distributed.run --nnodes=1 -
 run c2 --workload c2
 run c3 --workload c3
 run c4 --workload c4
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29515 bench.py --impl reference --gpus 2 --steps 1 --warmup 0 > $out/${tag}_bench_reference_2gpu.json 2> $out/${tag}_bench_reference_2gpu.log; echo "reference arm exit $?"; cut -c1-200 $out/${tag}_bench_reference_2gpu.json
