@@ -8,7 +8,9 @@
  * Conventions
  *   - every pointer is a DEVICE pointer unless the name ends in _host; the caller (torch) owns
  *     all buffers including workspaces; nothing in here allocates, frees or synchronises.
- *   - `stream` is a cudaStream_t passed as void*; work is stream-ordered and re-entrant.
+ *   - `stream` is a cudaStream_t passed as void*; work is stream-ordered.  Calls on different streams / devices may
+ *     overlap; the only process-wide state is (a) the option table below, (b) the launch counter, (c) per-(kernel, device)
+ *     "opt-in shared memory attribute set" flags, and (d) a few PV2_* development environment switches read once.
  *   - return value: 0 on success, a negative PV2_E* code for argument errors, a positive
  *     cudaError_t for launch errors.  pv2_error_string() maps either to text.
  *   - feature matrices are row-major [rows, channels] ("channels-last").
@@ -38,10 +40,13 @@ const char* pv2_error_string(int code);
 int64_t pv2_launch_count(void);
 /* Number of SMs the library sized its persistent grids for (148 on B200); 0 if no device. */
 int pv2_sm_count(void);
-/* Kernel-selection switches for A/B measurements and tests (defaults: environment PV2_GG_TMA / PV2_GG_BX3 / PV2_WGRAD_MN,
- * read once).  "gg_tma": bf16 gather through TMA gather4 (-1 auto by size, 0 off, 1 on); "gg_bx3": fp32 gather-GEMM as
- * bf16x3 (0 / 1); "wgrad_mn": MN-major bf16 weight-gradient kernel (0 / 1).  Results never depend on them beyond the
- * stated tolerances.  set: 0 / PV2_EINVAL; get: the value, -1 for an unknown name. */
+/* Kernel-selection switches for A/B measurements and tests (defaults from the environment, read once: PV2_GG_TMA,
+ * PV2_GG_BX3, PV2_WGRAD_MN, PV2_LINEAR_BX3, PV2_GG_KSPLIT_MAX, PV2_GG_GROUPS, PV2_GG_BX3_SPLIT).  "gg_tma": bf16 gather
+ * through TMA gather4 (-1 auto by size, 0 off, 1 on); "gg_bx3": fp32 gather-GEMM as bf16x3 (0 / 1); "wgrad_mn": MN-major
+ * bf16 weight-gradient kernel (0 / 1); "linear_bx3": render-MLP linears on the bf16x3 kernel (0 / 1); "gg_ksplit_max": cap
+ * of the split-K factor on the small levels (0 = none); "gg_bx3_split": small levels on the split-K bf16x3 kernel
+ * (default 0, measured slower); "gg_groups": reserved.  Results never depend on them beyond the stated tolerances.
+ * set: 0 / PV2_EINVAL; get: the value, -1 for an unknown name. */
 int pv2_set_option(const char* name, int value);
 int pv2_get_option(const char* name);
 
