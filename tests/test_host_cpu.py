@@ -322,3 +322,59 @@ def test_semantic_loss_matches_reference_golden():
     z = m._semantic_loss({"semantic": arr["out.semantic"]},
                          {"semantic": torch.zeros_like(arr["semantic_gt"]), "depth": arr["depth_gt"]})
     assert float(z) == 0.0
+
+
+def test_semantic_and_pdnorm_models_construct_through_registry():
+    """`PonderIndoor-v2` with the semantic branch (class embeddings handed in, PPT point loss) and with the SpUNet-v1m3
+    backbone builds from config dicts through the registry and exposes the reference's extra state (ponder_indoor_base.py:
+    66-118: `embedding_table`, `class_embedding`, `logit_scale`, `proj_head`)."""
+    from oracle.gen_golden import INDOOR_MODEL_CFG
+    from ponderv2_b200.models import MODELS
+    from tests.golden_util import product_renderer_cfg
+    rcfg = product_renderer_cfg(dict(kind="indoor", S0=96, Si=36, semantic=24))
+    cfg = dict(INDOOR_MODEL_CFG, renderer=rcfg, render_semantic=True, class_embedding=torch.randn(13, 24),
+               conditions=("ScanNet", "S3DIS"), valid_index=(tuple(range(13)), tuple(range(5))), ppt_loss_weight=1.0,
+               ppt_criteria=[dict(type="CrossEntropyLoss", loss_weight=1.0, ignore_index=-1)])
+    cfg["backbone"] = dict(type="SpUNet-v1m3", in_channels=6, num_classes=0, conditions=("ScanNet", "S3DIS"))
+    m = MODELS.build(cfg)
+    sd = m.state_dict()
+    assert type(m.backbone).__name__ == "SpUNetPDNorm"
+    for key in ("class_embedding", "logit_scale", "proj_head.weight", "embedding_table.weight",
+                "renderer.field.semantic_decoder.lin0.weight"):
+        assert key in sd, key
+    assert sd["class_embedding"].shape == (13, 24) and sd["proj_head.weight"].shape == (24, 96)
+    assert abs(float(sd["class_embedding"].norm(dim=-1).mean()) - 1.0) < 1e-5          # unit-norm rows, as load_semantic
+    table = m._class_table({"condition": ["S3DIS"]})
+    assert table.shape == (5, 24)
+    # without embeddings (and without CLIP in this image) construction must fail loudly, not silently skip the branch
+    bad = dict(cfg); bad.pop("class_embedding")
+    try:
+        MODELS.build(bad)
+    except RuntimeError as e:
+        assert "class_embedding" in str(e)
+    else:
+        try:
+            import clip  # noqa: F401
+        except ImportError:
+            raise AssertionError("render_semantic=True without embeddings must raise when CLIP is absent")
+
+
+def test_traffic_tool_books_render_linears_separately(tmp_path):
+    """tools/traffic_from_launches.py on the committed ncu launch list: the render-MLP linear launches (same kernel as the
+    sparse convolutions) are told apart by their position between the field kernels, so that bench.py's roofline.traffic
+    is the sparse convolutions' own DRAM traffic."""
+    import json
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    src = root / "profiles" / "r2zd_launches.csv"
+    out = tmp_path / "t.json"
+    subprocess.run([sys.executable, str(root / "tools" / "traffic_from_launches.py"), str(src), str(out)], check=True,
+                   capture_output=True)
+    k = json.loads(out.read_text())["kernels"]
+    lin = [v for n, v in k.items() if "[render linear]" in n]
+    assert sum(v["launches"] for v in lin) == 9                      # 2 coarse + 3 fine forward, 4 backward layers per step
+    conv = [v for n, v in k.items() if n.startswith("umma_gather_gemm") and "[render linear]" not in n]
+    per_launch = sum(v["dram_bytes_total"] for v in conv) / sum(v["launches"] for v in conv)
+    assert 5e6 < per_launch < 17.1e6                                 # below the 17.0 MB algorithmic bytes: L2 reuse
